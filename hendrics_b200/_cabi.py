@@ -1,0 +1,119 @@
+"""ctypes binding of ``libhxsearch.so`` (C ABI declared in ``include/hx_search.h``).
+
+There is NO CPU fallback: if the shared library is missing or a CUDA call fails, an
+exception is raised.  Nothing in this package imports ``oracle/``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libhxsearch.so")
+
+HX_OK = 0
+HX_ERR_ARG, HX_ERR_CUDA, HX_ERR_NOMEM, HX_ERR_RANGE, HX_ERR_INTERNAL = -1, -2, -3, -4, -5
+HX_FOLD_DEFAULT, HX_FOLD_FORCE_GENERIC, HX_FOLD_FORCE_SCRATCH = 0, 1, 2
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_u32p = ctypes.POINTER(ctypes.c_uint32)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_i64, _int, _uint, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_uint, ctypes.c_double, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol of include/hx_search.h
+SIGNATURES = {
+    "hx_version": (_int, []),
+    "hx_last_error": (ctypes.c_char_p, []),
+    "hx_device_count": (_int, [ctypes.POINTER(_int)]),
+    "hx_launch_count": (_i64, []),
+    "hx_fold_search": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _int, _uint, _c_dp, _c_u32p, _int]),
+    "hx_fold_search_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _uint, _vp, _vp, _vp]),
+    "hx_qffa_search": (_int, [_c_dp, _i64, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64, _int, _c_dp,
+                              _c_u32p, _int]),
+    "hx_qffa_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _i64, _int, _vp,
+                                  _vp, _vp]),
+    "hx_zn_unbinned": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _c_dp, _int]),
+    "hx_zn_unbinned_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),
+    "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
+    "hx_microbench": (_int, [_int, _int, _c_dp, _int]),
+}
+
+
+class HxError(RuntimeError):
+    """A libhxsearch call failed (bad argument, CUDA error, no device, ...)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libhxsearch error {code}: {msg}")
+        self.code = code
+
+
+class HxRangeError(HxError, ValueError):
+    pass
+
+
+_lib = None
+
+
+def build_library(force=False, quiet=True):
+    """(Re)build libhxsearch.so in-tree with nvcc for sm_100a."""
+    csrc = os.path.join(_PKG_DIR, "csrc")
+    cmd = ["make", "-C", csrc, "-j8"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL if quiet else None)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C hendrics_b200/csrc`. hendrics_b200 has no CPU fallback."
+            )
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != HX_OK:
+        msg = lib().hx_last_error().decode("utf-8", "replace")
+        if rc == HX_ERR_RANGE:
+            raise HxRangeError(rc, msg)
+        if rc == HX_ERR_ARG:
+            raise HxError(rc, msg)
+        raise HxError(rc, msg)
+
+
+def dptr(a, ctype=_c_dp):
+    return a.ctypes.data_as(ctype)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    n = _int(0)
+    rc = lib().hx_device_count(ctypes.byref(n))
+    return n.value if rc == HX_OK else 0
+
+
+def launch_count():
+    return int(lib().hx_launch_count())
+
+
+def microbench(kind, reps=5, device=0):
+    out = _dbl(0.0)
+    check(lib().hx_microbench(int(kind), int(reps), ctypes.byref(out), int(device)))
+    return out.value

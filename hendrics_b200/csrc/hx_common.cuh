@@ -1,0 +1,116 @@
+// Shared helpers for libhxsearch.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hx_search.h"
+
+namespace hx {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define HX_CUDA_TRY(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            hx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                        \
+            return (_e == cudaErrorMemoryAllocation) ? HX_ERR_NOMEM : HX_ERR_CUDA;          \
+        }                                                                                   \
+    } while (0)
+
+#define HX_CHECK_LAUNCH(name)                                                          \
+    do {                                                                               \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess) {                                                       \
+            hx::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));   \
+            return HX_ERR_CUDA;                                                        \
+        }                                                                              \
+        hx::count_launch();                                                            \
+    } while (0)
+
+// RAII device buffer for the host-pointer entry points.
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <typename T>
+    T *as() {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct DeviceInfo {
+    int sm_count;
+    int smem_optin;        // max dynamic shared memory per block (opt-in)
+    int smem_per_sm;       // shared memory per SM
+    int reserved_smem;     // reserved shared memory per block
+    uint32_t dyn_smem_base;  // shared-window address at which dynamic smem starts (no static smem)
+};
+// Cached per device; probes dyn_smem_base with a tiny kernel on first use.
+int get_device_info(int device, DeviceInfo *out);
+
+// ---- device-side PTX helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+
+// 1.5 * 2^52: adding it with round-toward-minus-infinity leaves floor(x) in the low mantissa bits
+// (two's complement) for |x| < 2^51.
+#define HX_MAGIC 6755399441055744.0
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr));
+}
+
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace hx

@@ -1,0 +1,606 @@
+// K1: exact (f, fdot) trial-grid fold search for sm_100a.
+//
+// Replaces the hot loop of stingray.pulse.search._folding_search (reached from
+// hendrics/efsearch.py:1179-1187 through z_n_search / epoch_folding_search):
+//   per trial:  _pulse_phase_fast -> _profile_fast -> ef_profile_stat | z_n_binned_events.
+//
+// Design ("K1"):
+//   * lane = trial.  Every thread owns R trials and, for each, a PRIVATE nbin-bin uint32 histogram
+//     column in shared memory laid out [bin][lane] (word address = bin*32 + lane), so that every
+//     histogram access of a warp hits 32 distinct banks: no atomics, no bank conflicts.
+//   * events stream HBM/L2 -> shared memory through a 2-stage cp.async.bulk (TMA engine) + mbarrier
+//     pipeline and are broadcast to all threads with one LDS.128 per event (pair).
+//   * phase arithmetic is the reference's, rounding for rounding: t*f and q*fd (q = (0.5*t)*t) are
+//     separately rounded products, added with one rounding -- never an FMA.  For power-of-two nbin the
+//     trial constants are pre-scaled by nbin*128 (exact), floor() is one round-down add of 1.5*2^52
+//     and the bin byte offset is one AND of the low mantissa word; it is OR-ed into the (aligned)
+//     column base.  Per event*trial: 2 DMUL + 2 DADD + LOP3 + LDS + IADD + STS.
+//   * two events are retired per read-modify-write round; equal bins are merged with a compare.
+//   * the statistic epilogue (chi^2 or binned Z^2_n) is fused when a CTA sees all events of its
+//     trials; otherwise counts are reduced into a [trial/32][bin][32] global scratch with coalesced
+//     RED.ADD and a second small kernel computes the statistics.
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "hx_common.cuh"
+
+namespace hx {
+
+constexpr int TILE_EV = 512;  // events per pipeline stage
+
+struct FoldArgs {
+    const double *ev;  // HAS_FD ? interleaved (t, q) : t
+    long long n_ev;
+    const double *freqs;
+    long long n_f;
+    const double *fdots;
+    long long n_trials;
+    int nbin;
+    int nharm;
+    uint32_t binmask;  // POW2: (nbin-1) << 7
+    double scale;      // POW2: nbin*128, generic: 1
+    double *stats;
+    uint32_t *scratch;  // null => fused epilogue
+    const double *tab;  // [2*nbin] cos, sin
+    int warps;
+    uint32_t hist_off, tile_off;
+    long long ev_per_split;
+    int *errflag;
+};
+
+template <bool HAS_FD, bool POW2>
+__device__ __forceinline__ uint32_t bin_addr(double t, double q, double fN, double fdN, uint32_t mask, int nbin,
+                                             uint32_t cb) {
+    double x = __dmul_rn(t, fN);
+    if (HAS_FD) x = __dadd_rn(x, __dmul_rn(q, fdN));
+    if (POW2) {
+        // x = nbin*128*phase exactly; floor -> low word; bits [7, 7+log2 nbin) are the bin
+        double y = __dadd_rd(x, HX_MAGIC);
+        uint32_t lo = (uint32_t)__double2loint(y);
+        return (lo & mask) | cb;
+    } else {
+        double fl = __dsub_rn(__dadd_rd(x, HX_MAGIC), HX_MAGIC);  // floor(x), exact
+        double fr = __dsub_rn(x, fl);                              // ph -= floor(ph)
+        double z = __dmul_rn(fr, (double)nbin);
+        int b = __double2loint(__dadd_rd(z, HX_MAGIC));  // floor(z), 0 <= z <= nbin
+        b = min(b, nbin - 1);                            // A4 clamp
+        return cb + ((uint32_t)b << 7);
+    }
+}
+
+// chi^2 / Z^2_n of one profile; `cnt(j)` returns the count of bin j
+template <typename F>
+__device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const double *ctab, const double *stab) {
+    double tot = 0.0;
+    for (int j = 0; j < nbin; j++) tot += (double)cnt(j);
+    if (nharm == 0) {
+        double mean = tot / (double)nbin;
+        double chi = 0.0;
+        for (int j = 0; j < nbin; j++) {
+            double d = (double)cnt(j) - mean;
+            chi += d * d / mean;
+        }
+        return chi;
+    }
+    double res = 0.0;
+    const bool p2 = (nbin & (nbin - 1)) == 0;
+    for (int k = 1; k <= nharm; k++) {
+        double c = 0.0, s = 0.0;
+        int idx = 0;
+        for (int j = 0; j < nbin; j++) {
+            double p = (double)cnt(j);
+            c += ctab[idx] * p;
+            s += stab[idx] * p;
+            idx += k;
+            if (p2)
+                idx &= nbin - 1;
+            else
+                idx %= nbin;
+        }
+        res += c * c + s * s;
+    }
+    return 2.0 / tot * res;
+}
+
+template <int R, bool HAS_FD, bool POW2>
+__global__ void __launch_bounds__(1024, 1) fold_kernel(const FoldArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t blk = (uint32_t)a.nbin << 7;  // bytes of one (warp, r) histogram block
+    const uint32_t hist = sbase + a.hist_off;
+    const uint32_t tileb = sbase + a.tile_off;
+    constexpr int EVB = HAS_FD ? 16 : 8;
+    constexpr uint32_t TILE_BYTES = TILE_EV * EVB;
+
+    if (POW2 && (hist & (blk - 1)) != 0) {  // host/device layout disagreement: refuse to compute
+        if (tid == 0) atomicExch(a.errflag, 1);
+        return;
+    }
+
+    // zero this CTA's histograms
+    {
+        const uint32_t nbytes = (uint32_t)a.warps * R * blk;
+        for (uint32_t o = tid * 4; o < nbytes; o += blockDim.x * 4) sts_u32(hist + o, 0u);
+    }
+
+    // trial constants
+    const long long tb = (long long)blockIdx.x * a.warps + warp;  // block of 32*R trials
+    double fN[R], fdN[R];
+    uint32_t cb[R];
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        long long g = (tb * R + r) * 32 + lane;
+        valid[r] = g < a.n_trials;
+        long long gi = valid[r] ? g : 0;
+        long long ifd = gi / a.n_f, jf = gi - ifd * a.n_f;
+        fN[r] = valid[r] ? __dmul_rn(a.freqs[jf], a.scale) : 0.0;
+        fdN[r] = (HAS_FD && valid[r]) ? __dmul_rn(a.fdots[ifd], a.scale) : 0.0;
+        cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * 4u;
+    }
+
+    // event range of this CTA
+    const long long e0 = (long long)blockIdx.y * a.ev_per_split;
+    const long long e1 = min(a.n_ev, e0 + a.ev_per_split);
+    const int ntiles = (e1 > e0) ? (int)((e1 - e0 + TILE_EV - 1) / TILE_EV) : 0;
+    const uint32_t bar[2] = {sbase, sbase + 8};
+
+    auto issue = [&](int it) {
+        const long long s = e0 + (long long)it * TILE_EV;
+        const int cnt = (int)min((long long)TILE_EV, e1 - s);
+        const uint32_t bytes = (uint32_t)cnt * EVB, bulk = bytes & ~15u;
+        const uint32_t dst = tileb + (uint32_t)(it & 1) * TILE_BYTES;
+        const char *src = reinterpret_cast<const char *>(a.ev) + s * EVB;
+        if (bulk) {
+            mbar_expect_tx(bar[it & 1], bulk);
+            bulk_g2s(dst, src, bulk, bar[it & 1]);
+        } else {
+            mbar_arrive(bar[it & 1]);
+        }
+        if (bytes != bulk) {  // odd trailing fp64 (t-only tiles): plain copy, published by the next barrier
+            double v = *reinterpret_cast<const double *>(src + bulk);
+            *reinterpret_cast<double *>(smem + a.tile_off + (uint32_t)(it & 1) * TILE_BYTES + bulk) = v;
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(bar[0], 1);
+        mbar_init(bar[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    __syncthreads();
+
+    const uint32_t mask = a.binmask;
+    const int nbin = a.nbin;
+
+    for (int it = 0; it < ntiles; it++) {
+        const int buf = it & 1;
+        mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
+        const int cnt = (int)min((long long)TILE_EV, e1 - (e0 + (long long)it * TILE_EV));
+        const unsigned char *tp = smem + a.tile_off + (uint32_t)buf * TILE_BYTES;
+
+        int e = 0;
+#pragma unroll 2
+        for (; e + 2 <= cnt; e += 2) {
+            double t0, q0, t1, q1;
+            if (HAS_FD) {
+                double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)e * 16);
+                double2 v1 = *reinterpret_cast<const double2 *>(tp + (size_t)e * 16 + 16);
+                t0 = v0.x, q0 = v0.y, t1 = v1.x, q1 = v1.y;
+            } else {
+                double2 v = *reinterpret_cast<const double2 *>(tp + (size_t)e * 8);
+                t0 = v.x, t1 = v.y, q0 = 0.0, q1 = 0.0;
+            }
+            uint32_t a0[R], a1[R], c0[R], c1[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                a0[r] = bin_addr<HAS_FD, POW2>(t0, q0, fN[r], fdN[r], mask, nbin, cb[r]);
+                a1[r] = bin_addr<HAS_FD, POW2>(t1, q1, fN[r], fdN[r], mask, nbin, cb[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) c0[r] = lds_u32(a0[r]);
+#pragma unroll
+            for (int r = 0; r < R; r++) c1[r] = lds_u32(a1[r]);
+#pragma unroll
+            for (int r = 0; r < R; r++) sts_u32(a0[r], c0[r] + 1u);
+#pragma unroll
+            for (int r = 0; r < R; r++) sts_u32(a1[r], c1[r] + 1u + (a0[r] == a1[r] ? 1u : 0u));
+        }
+        if (e < cnt) {
+            double t0, q0 = 0.0;
+            if (HAS_FD) {
+                double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)e * 16);
+                t0 = v0.x, q0 = v0.y;
+            } else {
+                t0 = *reinterpret_cast<const double *>(tp + (size_t)e * 8);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                uint32_t ad = bin_addr<HAS_FD, POW2>(t0, q0, fN[r], fdN[r], mask, nbin, cb[r]);
+                sts_u32(ad, lds_u32(ad) + 1u);
+            }
+        }
+        __syncthreads();  // every warp is done with `buf`
+        if (tid == 0 && it + 2 < ntiles) issue(it + 2);
+    }
+
+    if (a.scratch != nullptr) {
+        // partial counts -> global scratch [trial/32][bin][32], coalesced across the warp
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint32_t *dst = a.scratch + ((size_t)(tb * R + r) * nbin) * 32 + lane;
+            for (int j = 0; j < nbin; j++) {
+                uint32_t c = lds_u32(cb[r] + ((uint32_t)j << 7));
+                if (c) atomicAdd(dst + (size_t)j * 32, c);
+            }
+        }
+        return;
+    }
+
+    // fused epilogue: tables into the (now idle) tile region
+    double *tabs = reinterpret_cast<double *>(smem + a.tile_off);
+    for (int i = tid; i < 2 * nbin; i += blockDim.x) tabs[i] = a.tab[i];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (!valid[r]) continue;
+        const uint32_t base = cb[r];
+        double st = profile_stat([&](int j) { return lds_u32(base + ((uint32_t)j << 7)); }, nbin, a.nharm, tabs,
+                                 tabs + nbin);
+        a.stats[(tb * R + r) * 32 + lane] = st;
+    }
+}
+
+// scratch [trial/32][bin][32] -> stats (+ optional [trial][nbin] profiles)
+__global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restrict__ scratch, long long n_trials,
+                                                        int nbin, int nharm, const double *__restrict__ tab,
+                                                        double *__restrict__ stats, uint32_t *__restrict__ profiles) {
+    extern __shared__ double tabs[];
+    for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) tabs[i] = tab[i];
+    __syncthreads();
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_trials) return;
+    const uint32_t *src = scratch + (size_t)(g >> 5) * nbin * 32 + (g & 31);
+    stats[g] = profile_stat([&](int j) { return src[(size_t)j * 32]; }, nbin, nharm, tabs, tabs + nbin);
+    if (profiles)
+        for (int j = 0; j < nbin; j++) profiles[(size_t)g * nbin + j] = src[(size_t)j * 32];
+}
+
+// (t) -> interleaved (t, q = (0.5*t)*t); rounding identical to the reference's 0.5*t*t
+__global__ void prep_tq_kernel(const double *__restrict__ t, long long n, double2 *__restrict__ tq) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double v = t[i];
+        tq[i] = make_double2(v, __dmul_rn(__dmul_rn(0.5, v), v));
+    }
+}
+
+// min/max of an fp64 array (range checks for the fast path); out = {min, max}
+__global__ void minmax_kernel(const double *__restrict__ x, long long n, double *out) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = x[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        // fp64 atomic min/max through an order-preserving integer mapping:
+        // non-negative doubles keep their bit pattern, negative ones map to -(magnitude bits)
+        auto enc = [](double d) {
+            unsigned long long b = (unsigned long long)__double_as_longlong(d);
+            return (long long)((b >> 63) ? 0x8000000000000000ull - b : b);
+        };
+        atomicMin(reinterpret_cast<long long *>(out), enc(lo));
+        atomicMax(reinterpret_cast<long long *>(out) + 1, enc(hi));
+    }
+}
+static double dec_ordered(long long e) {
+    unsigned long long u = (unsigned long long)e;
+    unsigned long long b = (e < 0) ? 0x8000000000000000ull - u : u;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+// stream-ordered temporary, released on scope exit
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t s;
+    explicit AsyncBuf(cudaStream_t st) : s(st) {}
+    ~AsyncBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
+    template <typename T>
+    T *as() {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// ---- host side --------------------------------------------------------------------------------
+
+struct FoldPlan {
+    int R, W, ctas_per_sm;
+    uint32_t hist_off, tile_off, smem_bytes;
+};
+
+static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, bool pow2, bool has_fd, FoldPlan *p) {
+    const uint32_t blk = (uint32_t)nbin * 128u;
+    const uint32_t hist_bytes = (uint32_t)W * R * blk;
+    const uint32_t tile_region = std::max<uint32_t>(2u * TILE_EV * (has_fd ? 16 : 8), (uint32_t)nbin * 16u);
+    uint32_t hist_off, tile_off;
+    if (pow2) {
+        uint32_t abs0 = di.dyn_smem_base + 16;
+        uint32_t hist_abs = (abs0 + blk - 1) / blk * blk;
+        hist_off = hist_abs - di.dyn_smem_base;
+        tile_off = (hist_off - 16 >= tile_region) ? 16u : hist_off + hist_bytes;
+    } else {
+        hist_off = 16;
+        tile_off = hist_off + hist_bytes;
+    }
+    uint32_t total = std::max(hist_off + hist_bytes, tile_off + tile_region);
+    if (total > (uint32_t)di.smem_optin) return false;
+    int k_smem = di.smem_per_sm / (int)(total + di.reserved_smem);
+    int k_thr = 2048 / (32 * W);
+    int k = std::min(std::min(k_smem, k_thr), 32);
+    if (k < 1) return false;
+    p->R = R, p->W = W, p->ctas_per_sm = k;
+    p->hist_off = hist_off, p->tile_off = tile_off, p->smem_bytes = total;
+    return true;
+}
+
+typedef void (*fold_fn_t)(const FoldArgs);
+template <int R>
+static fold_fn_t pick_fold_R(bool has_fd, bool pow2) {
+    if (has_fd) return pow2 ? fold_kernel<R, true, true> : fold_kernel<R, true, false>;
+    return pow2 ? fold_kernel<R, false, true> : fold_kernel<R, false, false>;
+}
+static fold_fn_t pick_fold(int R, bool has_fd, bool pow2) {
+    switch (R) {
+        case 1: return pick_fold_R<1>(has_fd, pow2);
+        case 2: return pick_fold_R<2>(has_fd, pow2);
+        default: return pick_fold_R<4>(has_fd, pow2);
+    }
+}
+
+static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
+static int g_fold_W_override = 0;
+
+// cos/sin tables: 2*pi*arange(0, 1, 1/nbin) as hendrics/ffa.py:40,51
+static void host_tables(int nbin, std::vector<double> &tab) {
+    tab.resize(2 * (size_t)nbin);
+    const double step = 1.0 / nbin;
+    for (int j = 0; j < nbin; j++) {
+        double tw = (M_PI * 2) * (j * step);
+        tab[j] = cos(tw);
+        tab[nbin + j] = sin(tw);
+    }
+}
+
+int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
+                         const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
+                         uint32_t *d_profiles, cudaStream_t st) {
+    if (!d_times || !d_freqs || !d_fdots || !d_stats) {
+        set_error("hx_fold_search: null pointer argument");
+        return HX_ERR_ARG;
+    }
+    if (n_ev < 0 || n_f < 0 || n_fd < 0 || nbin < 2 || nbin > HX_MAX_NBIN || nharm < 0 || nharm > HX_MAX_NHARM) {
+        set_error("hx_fold_search: bad sizes (n_ev=%lld n_f=%lld n_fd=%lld nbin=%d nharm=%d)", (long long)n_ev,
+                  (long long)n_f, (long long)n_fd, nbin, nharm);
+        return HX_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_times) & 15) != 0) {
+        set_error("hx_fold_search_dev: d_times must be 16-byte aligned");
+        return HX_ERR_ARG;
+    }
+    const long long n_trials = (long long)n_f * n_fd;
+    if (n_trials == 0) return HX_OK;
+    int device;
+    HX_CUDA_TRY(cudaGetDevice(&device));
+    DeviceInfo di;
+    int rc = get_device_info(device, &di);
+    if (rc) return rc;
+
+    // ranges: [tmin,tmax, fmin,fmax, fdmin,fdmax]
+    AsyncBuf rng(st);
+    HX_CUDA_TRY(rng.alloc(6 * sizeof(long long) + sizeof(int)));
+    long long init[7];
+    for (int i = 0; i < 3; i++) init[2 * i] = INT64_MAX, init[2 * i + 1] = INT64_MIN;
+    init[6] = 0;
+    HX_CUDA_TRY(cudaMemcpyAsync(rng.p, init, sizeof(init) - 4, cudaMemcpyHostToDevice, st));
+    int *d_err = reinterpret_cast<int *>(rng.as<long long>() + 6);
+    if (n_ev > 0) {
+        minmax_kernel<<<(int)std::min<long long>((n_ev + 255) / 256, 1184), 256, 0, st>>>(d_times, n_ev,
+                                                                                          rng.as<double>());
+        HX_CHECK_LAUNCH("minmax_kernel");
+    }
+    minmax_kernel<<<(int)std::min<long long>((n_f + 255) / 256, 1184), 256, 0, st>>>(d_freqs, n_f,
+                                                                                     rng.as<double>() + 2);
+    HX_CHECK_LAUNCH("minmax_kernel");
+    minmax_kernel<<<1, 256, 0, st>>>(d_fdots, n_fd, rng.as<double>() + 4);
+    HX_CHECK_LAUNCH("minmax_kernel");
+    long long henc[6];
+    HX_CUDA_TRY(cudaMemcpyAsync(henc, rng.p, sizeof(henc), cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaStreamSynchronize(st));
+    double tmin = 0, tmax = 0;
+    if (n_ev > 0) tmin = dec_ordered(henc[0]), tmax = dec_ordered(henc[1]);
+    const double fmin = dec_ordered(henc[2]), fmax = dec_ordered(henc[3]);
+    const double fdmin = dec_ordered(henc[4]), fdmax = dec_ordered(henc[5]);
+    if (!(std::isfinite(tmin) && std::isfinite(tmax) && std::isfinite(fmin) && std::isfinite(fmax) &&
+          std::isfinite(fdmin) && std::isfinite(fdmax))) {
+        set_error("hx_fold_search: non-finite times / frequencies / fdots");
+        return HX_ERR_ARG;
+    }
+    const bool has_fd = !(fdmin == 0.0 && fdmax == 0.0);
+    const double tabs_ = std::max(std::fabs(tmin), std::fabs(tmax));
+    const double fabs_ = std::max(std::fabs(fmin), std::fabs(fmax));
+    const double fdabs_ = std::max(std::fabs(fdmin), std::fabs(fdmax));
+    const double phmax = tabs_ * fabs_ + 0.5 * tabs_ * tabs_ * fdabs_;
+    if (!(phmax < 1125899906842624.0 /* 2^50 */)) {
+        set_error("hx_fold_search: |phase| up to %.3g cycles exceeds the fp64 folding range (2^50)", phmax);
+        return HX_ERR_RANGE;
+    }
+    const bool nbin_p2 = (nbin & (nbin - 1)) == 0;
+    // fast path needs: power-of-two nbin, scaled phase inside the magic-add range, and provably
+    // non-negative phases (a negative phase in (-0.5, 0) is rounded by the reference's
+    // `ph - floor(ph)` before binning; the generic path reproduces that rounding).
+    bool nonneg = tmin >= 0 && fmin >= 0 && (fdmin >= 0 || fmin + 0.5 * tmax * fdmin * (1 + 1e-12) > 0);
+    bool pow2 = nbin_p2 && nonneg && phmax * nbin * 128.0 < 1125899906842624.0 && !(flags & HX_FOLD_FORCE_GENERIC);
+
+    // ---- plan -------------------------------------------------------------------------------
+    int R = g_fold_R_override ? g_fold_R_override : (nbin <= 32 ? 4 : 2);
+    FoldPlan best{};
+    int best_res = -1;
+    for (int W = 1; W <= 32; W++) {
+        FoldPlan p;
+        if (!plan_layout(di, nbin, R, W, pow2, has_fd, &p)) continue;
+        if (g_fold_W_override && W != g_fold_W_override) continue;
+        int res = p.ctas_per_sm * W;
+        if (res > best_res) best = p, best_res = res;  // ties: keep the smaller CTA (finer tail)
+    }
+    if (best_res < 0 && R > 1) {  // very large nbin: fall back to one trial per thread
+        R = 1;
+        for (int W = 1; W <= 32; W++) {
+            FoldPlan p;
+            if (!plan_layout(di, nbin, R, W, pow2, has_fd, &p)) continue;
+            int res = p.ctas_per_sm * W;
+            if (res > best_res) best = p, best_res = res;
+        }
+    }
+    if (best_res < 0) {
+        set_error("hx_fold_search: nbin=%d does not fit in shared memory", nbin);
+        return HX_ERR_ARG;
+    }
+    const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);
+    int W = best.W;
+    // few trials: shrink CTAs so that every SM gets one, then split the events across CTAs
+    {
+        long long want = (n_tb + di.sm_count - 1) / di.sm_count;
+        if (want < W) {
+            int Wn = (int)std::max<long long>(1, want);
+            FoldPlan p;
+            if (plan_layout(di, nbin, R, Wn, pow2, has_fd, &p)) best = p, W = Wn;
+        }
+    }
+    const long long n_cta_x = (n_tb + W - 1) / W;
+    const long long slots = (long long)di.sm_count * best.ctas_per_sm;
+    long long ev_splits = 1;
+    if (n_cta_x < slots && n_ev > 0) {
+        ev_splits = std::max<long long>(1, slots / n_cta_x);
+        ev_splits = std::min<long long>(ev_splits, std::max<long long>(1, n_ev / (4 * TILE_EV)));
+        ev_splits = std::min<long long>(ev_splits, 65535);
+    }
+    long long ev_per_split = (n_ev + ev_splits - 1) / std::max<long long>(ev_splits, 1);
+    ev_per_split = (ev_per_split + TILE_EV - 1) / TILE_EV * TILE_EV;
+    if (ev_per_split == 0) ev_per_split = TILE_EV;
+    ev_splits = std::max<long long>(1, (n_ev + ev_per_split - 1) / ev_per_split);
+    const bool fused = ev_splits == 1 && d_profiles == nullptr && !(flags & HX_FOLD_FORCE_SCRATCH);
+
+    // ---- device temporaries -----------------------------------------------------------------
+    AsyncBuf b_tq(st), b_tab(st), b_scratch(st);
+    std::vector<double> tab;
+    host_tables(nbin, tab);
+    HX_CUDA_TRY(b_tab.alloc(tab.size() * sizeof(double)));
+    HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *ev = d_times;
+    if (has_fd && n_ev > 0) {
+        HX_CUDA_TRY(b_tq.alloc((size_t)n_ev * 16));
+        prep_tq_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>(d_times, n_ev, b_tq.as<double2>());
+        HX_CHECK_LAUNCH("prep_tq_kernel");
+        ev = b_tq.as<double>();
+    }
+    if (!fused) {
+        size_t sbytes = (size_t)n_tb * R * nbin * 32 * sizeof(uint32_t);
+        HX_CUDA_TRY(b_scratch.alloc(sbytes));
+        HX_CUDA_TRY(cudaMemsetAsync(b_scratch.p, 0, sbytes, st));
+    }
+    void *d_tab = b_tab.p, *d_scratch = fused ? nullptr : b_scratch.p;
+
+    FoldArgs a{};
+    a.ev = ev, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots, a.n_trials = n_trials;
+    a.nbin = nbin, a.nharm = nharm;
+    a.binmask = pow2 ? (uint32_t)(nbin - 1) << 7 : 0u;
+    a.scale = pow2 ? (double)nbin * 128.0 : 1.0;
+    a.stats = d_stats, a.scratch = reinterpret_cast<uint32_t *>(d_scratch), a.tab = reinterpret_cast<double *>(d_tab);
+    a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
+    a.errflag = d_err;
+
+    fold_fn_t fn = pick_fold(R, has_fd, pow2);
+    HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem_bytes));
+    dim3 grid((unsigned)n_cta_x, (unsigned)ev_splits);
+    fn<<<grid, W * 32, best.smem_bytes, st>>>(a);
+    HX_CHECK_LAUNCH("fold_kernel");
+    if (!fused) {
+        fold_stat_kernel<<<(unsigned)((n_trials + 255) / 256), 256, 2 * nbin * sizeof(double), st>>>(
+            reinterpret_cast<uint32_t *>(d_scratch), n_trials, nbin, nharm, reinterpret_cast<double *>(d_tab), d_stats,
+            d_profiles);
+        HX_CHECK_LAUNCH("fold_stat_kernel");
+    }
+    int herr = 0;
+    HX_CUDA_TRY(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaStreamSynchronize(st));
+    if (herr) {
+        set_error("fold_kernel: shared-memory layout mismatch (dyn_smem_base probe wrong)");
+        return HX_ERR_INTERNAL;
+    }
+    return HX_OK;
+}
+
+}  // namespace hx
+
+extern "C" {
+
+int hx_fold_set_tuning(int R, int W) {
+    hx::g_fold_R_override = (R == 1 || R == 2 || R == 4) ? R : 0;
+    hx::g_fold_W_override = (W >= 1 && W <= 32) ? W : 0;
+    return HX_OK;
+}
+
+int hx_fold_search_dev(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
+                       const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
+                       uint32_t *d_profiles, void *stream) {
+    return hx::fold_search_dev_impl(d_times, n_ev, d_freqs, n_f, d_fdots, n_fd, nbin, nharm, flags, d_stats,
+                                    d_profiles, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hx_fold_search(const double *times, int64_t n_ev, const double *freqs, int64_t n_f, const double *fdots,
+                   int64_t n_fd, int nbin, int nharm, unsigned flags, double *stats, uint32_t *profiles, int device) {
+    if (!times || !freqs || !fdots || !stats) {
+        hx::set_error("hx_fold_search: null pointer argument");
+        return HX_ERR_ARG;
+    }
+    if (n_ev < 0 || n_f < 0 || n_fd < 0) {
+        hx::set_error("hx_fold_search: negative size");
+        return HX_ERR_ARG;
+    }
+    HX_CUDA_TRY(cudaSetDevice(device));
+    const size_t n_tr = (size_t)n_f * n_fd;
+    if (n_tr == 0) return HX_OK;
+    hx::DevBuf dt, df, dfd, ds, dp;
+    HX_CUDA_TRY(dt.alloc((size_t)n_ev * 8));
+    HX_CUDA_TRY(df.alloc((size_t)n_f * 8));
+    HX_CUDA_TRY(dfd.alloc((size_t)n_fd * 8));
+    HX_CUDA_TRY(ds.alloc(n_tr * 8));
+    if (profiles) HX_CUDA_TRY(dp.alloc(n_tr * nbin * 4));
+    HX_CUDA_TRY(cudaMemcpy(dt.p, times, (size_t)n_ev * 8, cudaMemcpyHostToDevice));
+    HX_CUDA_TRY(cudaMemcpy(df.p, freqs, (size_t)n_f * 8, cudaMemcpyHostToDevice));
+    HX_CUDA_TRY(cudaMemcpy(dfd.p, fdots, (size_t)n_fd * 8, cudaMemcpyHostToDevice));
+    int rc = hx::fold_search_dev_impl(dt.as<double>(), n_ev, df.as<double>(), n_f, dfd.as<double>(), n_fd, nbin, nharm,
+                                      flags, ds.as<double>(), profiles ? dp.as<uint32_t>() : nullptr, 0);
+    if (rc) return rc;
+    HX_CUDA_TRY(cudaMemcpy(stats, ds.p, n_tr * 8, cudaMemcpyDeviceToHost));
+    if (profiles) HX_CUDA_TRY(cudaMemcpy(profiles, dp.p, n_tr * nbin * 4, cudaMemcpyDeviceToHost));
+    return HX_OK;
+}
+
+}  // extern "C"

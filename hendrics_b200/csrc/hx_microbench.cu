@@ -1,0 +1,116 @@
+// Issue-rate microbenchmarks: the measured denominators of the K1 roofline (SURVEY.md 8d asks for
+// the FP64 pipe peak to be measured on the box, MEASURED_PEAKS.json has no FP64 entry).
+#include <algorithm>
+
+#include "hx_common.cuh"
+
+namespace hx {
+
+constexpr int MB_ITERS = 4096;
+constexpr int MB_ILP = 8;
+
+// kind 0: DFMA, kind 1: DMUL + DADD (what the parity kernels must issue: no contraction)
+template <int KIND>
+__global__ void __launch_bounds__(256) mb_fp64_kernel(double *out, double a, double b) {
+    double x[MB_ILP];
+#pragma unroll
+    for (int i = 0; i < MB_ILP; i++) x[i] = a + (double)(threadIdx.x + i);
+    for (int it = 0; it < MB_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < MB_ILP; i++) {
+            if (KIND == 0) {
+                x[i] = __fma_rn(x[i], a, b);
+            } else {
+                x[i] = __dadd_rn(__dmul_rn(x[i], a), b);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < MB_ILP; i++) s += x[i];
+    if (s == 1.2345e-300) out[0] = s;  // never true; keeps the chain alive
+}
+
+// kind 2: LDS + IADD + STS on private [bin][lane] columns (conflict-free); kind 3: red.shared.add
+template <int KIND>
+__global__ void __launch_bounds__(256) mb_smem_kernel(uint32_t *out, uint32_t seed) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const uint32_t base = smem_u32(dsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // 4 columns of 16 bins per thread: block of 16*128 B per (warp, column)
+    uint32_t cb[4];
+    for (int c = 0; c < 4; c++) cb[c] = base + (uint32_t)(warp * 4 + c) * 2048u + lane * 4u;
+    for (int c = 0; c < 4; c++)
+        for (int j = 0; j < 16; j++) sts_u32(cb[c] + j * 128, 0u);
+    uint32_t r = seed * 747796405u + threadIdx.x * 2891336453u + 1u;
+    for (int it = 0; it < MB_ITERS; it++) {
+        r = r * 1664525u + 1013904223u;
+        uint32_t a0 = cb[0] + ((r >> 4) & 0x780u), a1 = cb[1] + ((r >> 9) & 0x780u);
+        uint32_t a2 = cb[2] + ((r >> 14) & 0x780u), a3 = cb[3] + ((r >> 19) & 0x780u);
+        if (KIND == 2) {
+            uint32_t c0 = lds_u32(a0), c1 = lds_u32(a1), c2 = lds_u32(a2), c3 = lds_u32(a3);
+            sts_u32(a0, c0 + 1), sts_u32(a1, c1 + 1), sts_u32(a2, c2 + 1), sts_u32(a3, c3 + 1);
+        } else {
+            red_shared_inc(a0), red_shared_inc(a1), red_shared_inc(a2), red_shared_inc(a3);
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int c = 0; c < 4; c++)
+        for (int j = 0; j < 16; j++) s += lds_u32(cb[c] + j * 128);
+    if (s != 4u * MB_ITERS) atomicAdd(out, 1u);  // counts are conserved: also a correctness check
+}
+
+}  // namespace hx
+
+extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) {
+    using namespace hx;
+    if (!ops_per_s || kind < 0 || kind > 3 || reps < 1) {
+        set_error("hx_microbench: bad arguments");
+        return HX_ERR_ARG;
+    }
+    HX_CUDA_TRY(cudaSetDevice(device));
+    DeviceInfo di;
+    int rc = get_device_info(device, &di);
+    if (rc) return rc;
+    DevBuf out;
+    HX_CUDA_TRY(out.alloc(64));
+    HX_CUDA_TRY(cudaMemset(out.p, 0, 64));
+    cudaEvent_t e0, e1;
+    HX_CUDA_TRY(cudaEventCreate(&e0));
+    HX_CUDA_TRY(cudaEventCreate(&e1));
+    const int threads = 256;
+    const int grid = di.sm_count * 8 * 4;  // 4 waves of 8 CTAs/SM
+    const size_t smem = (kind >= 2) ? (size_t)(threads / 32) * 4 * 2048 : 0;
+    if (kind == 2) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kind == 3) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    double best_ms = 1e30;
+    for (int r = 0; r < reps + 1; r++) {  // first rep is a warm-up
+        HX_CUDA_TRY(cudaEventRecord(e0));
+        switch (kind) {
+            case 0: mb_fp64_kernel<0><<<grid, threads>>>(out.as<double>() + 1, 1.0000001, 1e-9); break;
+            case 1: mb_fp64_kernel<1><<<grid, threads>>>(out.as<double>() + 1, 1.0000001, 1e-9); break;
+            case 2: mb_smem_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
+            default: mb_smem_kernel<3><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
+        }
+        HX_CHECK_LAUNCH("microbench kernel");
+        HX_CUDA_TRY(cudaEventRecord(e1));
+        HX_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        HX_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) best_ms = std::min(best_ms, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    uint32_t bad = 0;
+    HX_CUDA_TRY(cudaMemcpy(&bad, out.p, 4, cudaMemcpyDeviceToHost));
+    if (kind >= 2 && bad) {
+        set_error("hx_microbench: shared-memory counters not conserved (%u warps)", bad);
+        return HX_ERR_INTERNAL;
+    }
+    double per_thread = (kind == 0) ? (double)MB_ITERS * MB_ILP
+                      : (kind == 1) ? (double)MB_ITERS * MB_ILP * 2
+                                    : (double)MB_ITERS * 4;
+    *ops_per_s = per_thread * threads * (double)grid / (best_ms * 1e-3);
+    return HX_OK;
+}

@@ -1,0 +1,200 @@
+"""Drop-in replacements for ``stingray.pulse.search.z_n_search`` / ``epoch_folding_search``.
+
+These are the two module-level names HENDRICS imports at ``hendrics/efsearch.py:15-18`` and
+passes as ``func=`` to ``folding_search`` (``hendrics/efsearch.py:1141-1193``).  Signatures,
+keyword names, return shapes and error behaviour follow the upstream functions (SURVEY.md
+section 8b / Appendix A); the per-trial fold + statistic runs in the sm_100a kernel K1
+(``csrc/hx_fold.cu``) through the C ABI (``include/hx_search.h``).
+
+Host code here is plumbing only: event selection per segment (half-open mask, like upstream),
+device buffers (torch), and the call into ``hx_fold_search_dev``.  No CPU fallback exists.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _cabi
+
+__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "z_n_search_unbinned"]
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise _cabi.HxError(_cabi.HX_ERR_CUDA, "no CUDA device available; hendrics_b200 has no CPU fallback")
+    return torch
+
+
+def _device(device):
+    torch = _torch()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _aligned(t):
+    """K1 streams events with 16-byte bulk copies: the first element must be 16-byte aligned."""
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def fold_stats_device(ts_d, freqs_d, fdots_d, nbin, nharm, flags=0, want_profiles=False):
+    """One K1 call on device tensors.  Returns stats (n_fd, n_f) [and uint32-valued profiles
+    (n_fd, n_f, nbin) as an int32 tensor]."""
+    torch = _torch()
+    n_f, n_fd = freqs_d.numel(), fdots_d.numel()
+    stats = torch.empty((n_fd, n_f), dtype=torch.float64, device=ts_d.device)
+    prof = torch.empty((n_fd, n_f, nbin), dtype=torch.int32, device=ts_d.device) if want_profiles else None
+    ts_d = _aligned(ts_d.contiguous())
+    with torch.cuda.device(ts_d.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _cabi.lib().hx_fold_search_dev(
+            ts_d.data_ptr(), ts_d.numel(), freqs_d.data_ptr(), n_f, fdots_d.data_ptr(), n_fd, int(nbin), int(nharm),
+            int(flags), stats.data_ptr(), prof.data_ptr() if want_profiles else None, stream,
+        )
+    _cabi.check(rc)
+    return (stats, prof) if want_profiles else stats
+
+
+def _folding_search(
+    nharm,
+    times,
+    frequencies,
+    nbin=128,
+    segment_size=np.inf,
+    fdots=0,
+    device=None,
+    flags=0,
+    return_profiles=False,
+):
+    """Upstream ``_folding_search`` fast branch with the (fdot, f) double loop
+    replaced by one K1 launch per segment."""
+    torch = _torch()
+    dev = _device(device)
+    frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
+    fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    times = np.asanyarray(times)
+    if times.size == 0:
+        raise ValueError("No events to fold")
+    times = (times - times[0]).astype(np.float64)  # A1: re-zero to the first event
+    length = times[-1]
+    if length < segment_size:
+        segment_size = length
+    start_times = np.arange(times[0], times[-1], segment_size)
+
+    times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
+    freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
+    fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
+    stats_d = torch.zeros(fgrid.shape, dtype=torch.float64, device=dev)
+    prof_d = torch.zeros(fgrid.shape + (nbin,), dtype=torch.int64, device=dev) if return_profiles else None
+    count = 0
+    for s in start_times:
+        good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open
+        ts_d = times_d[good]
+        n_good = ts_d.numel()
+        if n_good < 1:
+            continue
+        span = float(ts_d[-1] - ts_d[0])
+        if span < 0.2 * segment_size:
+            continue
+        res = fold_stats_device(ts_d, freqs_d, fdots_d, nbin, nharm, flags=flags, want_profiles=return_profiles)
+        if return_profiles:
+            stats_d += res[0]
+            prof_d += res[1].to(torch.int64) & 0xFFFFFFFF
+        else:
+            stats_d += res
+        count += 1
+    stats = stats_d.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        stats = stats / count
+    if fgrid.shape[0] == 1:
+        out = (fgrid.flatten(), stats.flatten())
+    else:
+        out = (fgrid, fdgrid, stats)
+    if return_profiles:
+        out = out + (prof_d.cpu().numpy(),)
+    return out
+
+
+def _check_branch(expocorr, weights, gti, what):
+    if expocorr and gti is None:
+        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    if expocorr or isinstance(weights, Iterable):
+        raise NotImplementedError(
+            f"{what}: the exposure-corrected / weighted `fold_events` branch is outside the B200 hot path "
+            "(SURVEY.md section 8f, rank 3); only the unweighted fast branch is implemented."
+        )
+
+
+def epoch_folding_search(
+    times, frequencies, nbin=128, segment_size=np.inf, expocorr=False, gti=None, weights=1, fdots=0, **kwargs
+):
+    """Epoch-folding chi^2 periodogram.  Same call as ``stingray.pulse.search.epoch_folding_search``.
+
+    Returns ``(fgrid, stats)`` (1-D) when a single fdot is searched, else
+    ``(fgrid, fdgrid, stats)`` of shape ``(n_fdot, n_freq)``."""
+    _check_branch(expocorr, weights, gti, "epoch_folding_search")
+    return _folding_search(0, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
+
+
+def z_n_search(
+    times,
+    frequencies,
+    nharm=4,
+    nbin=128,
+    segment_size=np.inf,
+    expocorr=False,
+    weights=1,
+    gti=None,
+    fdots=0,
+    **kwargs,
+):
+    """Binned Z^2_n periodogram.  Same call as ``stingray.pulse.search.z_n_search``."""
+    _check_branch(expocorr, weights, gti, "z_n_search")
+    if nharm < 1:
+        raise ValueError("nharm must be >= 1")
+    return _folding_search(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
+
+
+def fold_profiles(times, frequencies, fdots=0, nbin=128, nharm=0, device=None, flags=0):
+    """Profiles AND statistics of one fold over already-selected, already-zeroed times.
+
+    Returns ``(stats (n_fd, n_f), profiles (n_fd, n_f, nbin) int64)``; used by the parity tests
+    for the bit-exact profile-count check."""
+    torch = _torch()
+    dev = _device(device)
+    ts_d = torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(dev)
+    f_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(frequencies), dtype=np.float64)).to(dev)
+    fd_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(fdots), dtype=np.float64)).to(dev)
+    stats, prof = fold_stats_device(ts_d, f_d, fd_d, nbin, nharm, flags=flags, want_profiles=True)
+    return stats.cpu().numpy(), (prof.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+
+
+def z_n_search_unbinned(times, frequencies, nharm=2, fdots=0, device=None):
+    """Unbinned Z^2_n (extension, K4): oracle formula ``hendrics/efsearch.py:366-404`` with unit
+    weights.  Same return convention as ``z_n_search``."""
+    torch = _torch()
+    dev = _device(device)
+    frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
+    fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    ts_d = torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(dev)
+    f_d = torch.from_numpy(frequencies).to(dev)
+    fd_d = torch.from_numpy(fdots).to(dev)
+    stats = torch.empty(fgrid.shape, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().hx_zn_unbinned_dev(
+            ts_d.data_ptr(), ts_d.numel(), f_d.data_ptr(), f_d.numel(), fd_d.data_ptr(), fd_d.numel(), int(nharm),
+            stats.data_ptr(), torch.cuda.current_stream().cuda_stream,
+        )
+    _cabi.check(rc)
+    stats = stats.cpu().numpy()
+    if fgrid.shape[0] == 1:
+        return fgrid.flatten(), stats.flatten()
+    return fgrid, fdgrid, stats

@@ -1,0 +1,131 @@
+/*
+ * hx_search.h -- C ABI of libhxsearch.so, the B200 (sm_100a) pulsar periodicity-search library.
+ *
+ * Drop-in boundary for ONE hot path of StingraySoftware/HENDRICS: the (f, fdot) trial-grid
+ * Z^2_n / epoch-folding search behind HENzsearch / HENefsearch, including `--fast`.
+ * The reference is pure Python and has no FFI for this path; each entry
+ * point below cites the reference interface (relative to the HENDRICS tree) that a maintainer
+ * would rebind to it -- the ctypes stubs are in INTEGRATION.md and hendrics_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer; inputs are never modified;
+ *   - every function returns HX_OK (0) or a negative HX_ERR_* code; hx_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - functions without a `_dev` suffix take HOST pointers and perform H2D copy, kernels and D2H
+ *     copy synchronously on `device`;
+ *   - `_dev` functions take DEVICE pointers (resident on the current device of `stream`), only
+ *     enqueue work on `stream` (a cudaStream_t cast to void*, NULL = default stream) and do not
+ *     synchronize, except where stated;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     HX_ERR_CUDA.
+ */
+#ifndef HX_SEARCH_H
+#define HX_SEARCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HX_OK 0
+#define HX_ERR_ARG (-1)    /* invalid argument (null pointer, nbin out of range, ...) */
+#define HX_ERR_CUDA (-2)   /* CUDA runtime / launch failure, or no device */
+#define HX_ERR_NOMEM (-3)  /* device or host allocation failed */
+#define HX_ERR_RANGE (-4)  /* |phase| too large for fp64 folding (>= 2^51 cycles) */
+#define HX_ERR_INTERNAL (-5)
+
+#define HX_MAX_NBIN 1024 /* phase bins per profile, 2 <= nbin <= HX_MAX_NBIN */
+#define HX_MAX_NHARM 64
+
+/* flags for hx_fold_search* */
+#define HX_FOLD_DEFAULT 0u
+#define HX_FOLD_FORCE_GENERIC 1u /* disable the power-of-two-nbin fast path (testing) */
+#define HX_FOLD_FORCE_SCRATCH 2u /* disable the fused epilogue (testing) */
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+/* Version of this ABI (major*1000 + minor). */
+int hx_version(void);
+/* Message for the last error raised on the calling thread ("" if none). */
+const char *hx_last_error(void);
+/* Number of CUDA devices visible (0 and HX_ERR_CUDA when there is none). */
+int hx_device_count(int *count);
+/* Number of this library's kernel launches so far in this process (bench evidence). */
+int64_t hx_launch_count(void);
+
+/* ---- K1: exact fold search ---------------------------------------------------------------
+ * Replaces the inner loop of stingray.pulse.search._folding_search as driven by
+ * z_n_search / epoch_folding_search (imported at hendrics/efsearch.py:15-18, called at
+ * hendrics/efsearch.py:1179-1187): for every trial (fdots[i], freqs[j]) fold all events into an
+ * nbin-bin phase histogram (phase = t*f + 0.5*t*t*fd, separately rounded fp64, no FMA) and
+ * reduce it to
+ *     nharm == 0 : epoch-folding chi^2   = sum_j (p_j - mean)^2 / mean
+ *     nharm >= 1 : binned Z^2_nharm      (formula of hendrics/ffa.py:139-157)
+ *
+ *   times    [n_ev]        event times, already re-zeroed and segment-selected by the caller
+ *   freqs    [n_f], fdots [n_fd]
+ *   stats    [n_fd * n_f]  row-major (fdot, freq); overwritten
+ *   profiles [n_fd * n_f * nbin] uint32 counts, or NULL when not wanted
+ */
+int hx_fold_search(const double *times, int64_t n_ev, const double *freqs, int64_t n_f, const double *fdots,
+                   int64_t n_fd, int nbin, int nharm, unsigned flags, double *stats, uint32_t *profiles,
+                   int device);
+
+/* Same on device-resident buffers.  `d_times` must be 16-byte aligned. */
+int hx_fold_search_dev(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
+                       const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
+                       uint32_t *d_profiles, void *stream);
+
+/* ---- K2 + K3: one centre step of the `--fast` quasi-fast-folding search ------------------
+ * Replaces hendrics/efsearch.py:876-925 (search_with_qffa_step) = _fast_phase* (:854-873) +
+ * histogram2d (hendrics/base.py:667-693) + _fast_step (:817-851) for `n_centres` centre
+ * frequencies in one pass over the events.
+ *
+ *   times_c   [n_ev]  times minus the mid-time, fp64, sorted ascending
+ *   mean_f/mean_fd/mean_fdd [n_centres]
+ *   L, Q      [n_lq]  bin-shift pairs (the meshgrid of efsearch.py:921, flattened row-major)
+ *   stats     [n_centres * n_lq]
+ *   profiles  [n_centres * nprof * nbin] uint32 2-D profiles (time slice, phase bin), or NULL
+ */
+int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, const double *mean_fd,
+                   const double *mean_fdd, int64_t n_centres, int nbin, int nprof, const double *L, const double *Q,
+                   int64_t n_lq, int nharm, double *stats, uint32_t *profiles, int device);
+
+int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last, const double *d_mean_f,
+                       const double *d_mean_fd, const double *d_mean_fdd, int64_t n_centres, int nbin, int nprof,
+                       const double *d_L, const double *d_Q, int64_t n_lq, int nharm, double *d_stats,
+                       uint32_t *d_profiles, void *stream);
+
+/* ---- K4: unbinned Z^2_n (extension; oracle formula hendrics/efsearch.py:366-404) ---------
+ * stats[i*n_f + j] = 2/N * sum_{k=1..nharm} [(sum cos 2 pi k phi)^2 + (sum sin 2 pi k phi)^2]
+ * with phi = frac(t*f + 0.5*t*t*fd) per event.
+ */
+int hx_zn_unbinned(const double *times, int64_t n_ev, const double *freqs, int64_t n_f, const double *fdots,
+                   int64_t n_fd, int nharm, double *stats, int device);
+int hx_zn_unbinned_dev(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
+                       const double *d_fdots, int64_t n_fd, int nharm, double *d_stats, void *stream);
+
+/* ---- top-k candidates ----------------------------------------------------------------------
+ * Replaces the argpartition branch of hendrics/base.py:1140-1146 (find_peaks_in_image):
+ * the k largest entries of stats[n], value descending, ties by ascending flat index.
+ * idx/val have room for k entries; *n_out = min(k, n).
+ */
+int hx_topk(const double *stats, int64_t n, int k, int64_t *idx, double *val, int64_t *n_out, int device);
+int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double *h_val, int64_t *n_out,
+                void *stream); /* synchronizes `stream`; idx/val are HOST buffers */
+
+/* ---- measurement helpers --------------------------------------------------------------------
+ * FP64 pipe issue-rate microbenchmarks used as the roofline denominator:
+ *   kind 0: dependent-free DFMA chain      -> *ops_per_s = FP64 instructions/s (1 per DFMA)
+ *   kind 1: DMUL + DADD pairs (no FMA)     -> FP64 instructions/s
+ *   kind 2: shared-memory LDS+IADD+STS read-modify-write, conflict-free -> RMW/s
+ *   kind 3: shared-memory atomic add, conflict-free                     -> atomics/s
+ * Runs on `device`, blocks, returns the best of `reps` timings.
+ */
+int hx_microbench(int kind, int reps, double *ops_per_s, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HX_SEARCH_H */

@@ -1,0 +1,680 @@
+"""CPU ORACLE for the HENDRICS pulsar periodicity-search hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it.  The product (``hendrics_b200``) never does: it fails loudly when
+its CUDA library is missing.
+
+What it restates (file:line are relative to the reference tree, ``/root/reference``):
+
+* in-tree, read directly:
+    hendrics/efsearch.py:345-363   ``mod`` / ``shift_and_sum``
+    hendrics/efsearch.py:366-404   ``z_n_fast``                    (unbinned-capable Z^2_n)
+    hendrics/efsearch.py:817-851   ``_fast_step``
+    hendrics/efsearch.py:854-873   ``_fast_phase`` / ``_fast_phase_fdot`` / ``_fast_phase_fddot``
+    hendrics/efsearch.py:876-925   ``search_with_qffa_step``
+    hendrics/efsearch.py:928-1089  ``search_with_qffa``
+    hendrics/efsearch.py:1141-1193 ``folding_search``
+    hendrics/efsearch.py:199-205   ``check_phase_error_after_casting_to_double``
+    hendrics/ffa.py:38-157         cached harmonics, ``_z_n_fast_cached`` (binned Z^2_n)
+    hendrics/base.py:667-693       ``_hist2d_numba_seq`` / ``hist2d_numba_seq``
+    hendrics/base.py:1109-1148     ``find_peaks_in_image`` (rough / no-skimage branch)
+* out-of-tree (third-party dependency ``stingray>=2.3.2``, pyproject.toml:41, imported at
+  hendrics/efsearch.py:15-18; its source is NOT under /root/reference and it is not
+  installable here): ``stingray.pulse.search._folding_search / z_n_search /
+  epoch_folding_search / _pulse_phase_fast / _profile_fast`` and
+  ``stingray.pulse.pulsar.ef_profile_stat / z_n_binned_events``, restated from the
+  published stingray 2.x algorithm.
+
+PARITY STATUS: **parity unpinned at the stingray boundary** -- the reference's own
+tests hold no golden vector for z_n_search/epoch_folding_search (unseeded inputs, 1/T
+tolerances).  What *is* pinned, in tests/test_oracle.py, are the
+reference's doctest known answers (Z^2_n == 50 for the 1+sin profile, histogram ==
+np.histogram2d on in-range data, toy-image top-2 peaks, ...).
+
+Declared upstream ambiguities:
+  A1  ``rezero_to_first_event``  times -= times[0] inside ``_folding_search``      (default True)
+  A2  ``drop_last_event``        segment mask is half-open => t == t[-1] dropped   (default True)
+  A3  fdot term evaluated as ((0.5*t)*t)*fd, each product separately rounded       (no FMA)
+  A4  a phase that rounds to exactly 1.0 (or phase*nbin == nbin for non power-of-two nbin)
+      makes upstream's bincount one element too long; here the count is clamped into bin nbin-1.
+
+numba is used when importable (like the reference's hendrics/compat/compatibility.py:6-52),
+otherwise the same bodies run as plain Python/numpy.
+"""
+
+from __future__ import annotations
+
+import copy
+import math
+import warnings
+
+import numpy as np
+
+try:  # same policy as hendrics/compat/compatibility.py:6-52
+    from numba import njit, prange
+
+    HAS_NUMBA = True
+except Exception:  # pragma: no cover - numba is present in this image
+    HAS_NUMBA = False
+
+    def njit(*args, **kwargs):
+        if len(args) == 1 and callable(args[0]) and not kwargs:
+            return args[0]
+
+        def deco(f):
+            return f
+
+        return deco
+
+    prange = range
+
+
+# --------------------------------------------------------------------------------------
+# stingray.pulse.search._pulse_phase_fast / _profile_fast  [UPSTREAM-RECALLED, Appendix A]
+# --------------------------------------------------------------------------------------
+@njit()
+def pulse_phase_fast(time, f, fdot, buffer_array):
+    """phase = t*f + 0.5*t*t*fdot ; phase -= floor(phase)   (separately rounded, A3)."""
+    for i in range(len(time)):
+        buffer_array[i] = time[i] * f + 0.5 * time[i] * time[i] * fdot
+        buffer_array[i] -= np.floor(buffer_array[i])
+    return buffer_array
+
+
+@njit()
+def profile_fast(phase, nbin):
+    """int64 histogram of floor(phase*nbin); overflow clamped into nbin-1 (A4)."""
+    prof = np.zeros(nbin, dtype=np.int64)
+    for i in range(len(phase)):
+        b = np.int64(np.floor(phase[i] * nbin))
+        if b >= nbin:
+            b = nbin - 1
+        if b < 0:
+            b = 0
+        prof[b] += 1
+    return prof
+
+
+def profile_fast_upstream(phase, nbin):
+    """The literal upstream formulation (sentinel + bincount); used to show that
+    ``profile_fast`` equals it whenever no phase rounds up to the right edge."""
+    phase_bin = np.zeros(len(phase) + 2, dtype=np.int64)
+    phase_bin[-1] = nbin - 1
+    phase_bin[: len(phase)] = np.floor(phase * nbin).astype(np.int64)
+    bc = np.bincount(phase_bin)
+    bc[0] -= 1
+    bc[-1] -= 1
+    return bc
+
+
+# --------------------------------------------------------------------------------------
+# stingray.pulse.pulsar.ef_profile_stat / z_n_binned_events   [UPSTREAM-RECALLED]
+# in-tree twin of the Z formula: hendrics/ffa.py:38-157
+# --------------------------------------------------------------------------------------
+def ef_profile_stat(profile, err=None):
+    """chi^2 = sum((p - mean)^2 / err^2), err = sqrt(mean) by default."""
+    profile = np.asarray(profile, dtype=np.float64)
+    mean = np.mean(profile)
+    if err is None:
+        err = np.sqrt(mean)
+    return np.sum((profile - mean) ** 2 / err**2)
+
+
+def cached_sin_harmonics(nbin, z_n_n):
+    """hendrics/ffa.py:38-46."""
+    twopiphases = np.pi * 2 * np.arange(nbin) * (1.0 / nbin)
+    return np.tile(np.sin(twopiphases), z_n_n)
+
+
+def cached_cos_harmonics(nbin, z_n_n):
+    """hendrics/ffa.py:49-56."""
+    twopiphases = np.pi * 2 * np.arange(nbin) * (1.0 / nbin)
+    return np.tile(np.cos(twopiphases), z_n_n)
+
+
+@njit()
+def _z_n_fast_cached(norm, cached_sin, cached_cos, n=2):
+    """hendrics/ffa.py:59-104 -- Z^2_n of a binned profile, harmonic k read as the
+    stride-k slice of the n-times tiled table."""
+    total_norm = np.sum(norm)
+    result = 0.0
+    N = norm.size
+    for k in range(1, n + 1):
+        result += (
+            np.sum(cached_cos[: N * k : k] * norm) ** 2
+            + np.sum(cached_sin[: N * k : k] * norm) ** 2
+        )
+    return 2 / total_norm * result
+
+
+def z_n_fast_cached(norm, n=2):
+    """hendrics/ffa.py:107-136."""
+    norm = np.asarray(norm, dtype=np.float64)
+    return _z_n_fast_cached(norm, cached_sin_harmonics(norm.size, n), cached_cos_harmonics(norm.size, n), n)
+
+
+@njit()
+def _z_n_fast_cached_all(norm, cached_sin, cached_cos, ks):
+    """hendrics/ffa.py:139-157."""
+    total_norm = np.sum(norm)
+    all_zs = np.zeros(ks.size)
+    N = norm.size
+    total_sum = 0.0
+    for k in ks:
+        local_z = (
+            np.sum(cached_cos[: N * k : k] * norm) ** 2
+            + np.sum(cached_sin[: N * k : k] * norm) ** 2
+        )
+        all_zs[k - 1] = local_z + total_sum
+        total_sum += local_z
+    return 2 / total_norm * all_zs
+
+
+def z_n_fast_cached_all(norm, nmax=20):
+    """hendrics/ffa.py:160-194."""
+    norm = np.asarray(norm, dtype=np.float64)
+    ks = np.arange(1, nmax + 1, dtype=np.int64)
+    return ks, _z_n_fast_cached_all(
+        norm, cached_sin_harmonics(norm.size, nmax), cached_cos_harmonics(norm.size, nmax), ks
+    )
+
+
+def h_test(norm, nmax=20):
+    """hendrics/ffa.py:197-211."""
+    ks, zs = z_n_fast_cached_all(norm, nmax=nmax)
+    hs = zs - 4 * ks + 4
+    idx = np.argmax(hs)
+    return hs[idx], ks[idx]
+
+
+def z_n_binned_events(profile, n):
+    """stingray.pulse.pulsar.z_n_binned_events: same formula as hendrics/ffa.py:139-157."""
+    return z_n_fast_cached(np.asarray(profile, dtype=np.float64), n)
+
+
+@njit(fastmath=True)
+def z_n_fast(phase, norm, n=2):
+    """hendrics/efsearch.py:366-404 (k*phi by repeated addition)."""
+    total_norm = np.sum(norm)
+    result = 0.0
+    kph = np.zeros_like(phase)
+    for k in range(1, n + 1):
+        kph += phase
+        result += np.sum(np.cos(kph) * norm) ** 2 + np.sum(np.sin(kph) * norm) ** 2
+    return 2 / total_norm * result
+
+
+def z_n_events(phase, n):
+    """Unbinned Z^2_n of photon phases (cycles); oracle of the ``binned=False`` extension:
+    hendrics/efsearch.py:366-404 with norm == 1, evaluated without fastmath."""
+    ph = 2 * np.pi * np.asarray(phase, dtype=np.float64)
+    res = 0.0
+    for k in range(1, n + 1):
+        res += np.sum(np.cos(k * ph)) ** 2 + np.sum(np.sin(k * ph)) ** 2
+    return 2.0 / ph.size * res
+
+
+# --------------------------------------------------------------------------------------
+# stingray.pulse.search._folding_search / z_n_search / epoch_folding_search
+# --------------------------------------------------------------------------------------
+def select_segments(times, segment_size=np.inf, rezero_to_first_event=True, drop_last_event=True):
+    """Event selection of upstream ``_folding_search`` (Appendix A: A1, A2).
+
+    Returns the re-zeroed float64 times and the list of boolean masks of the segments
+    that are actually folded."""
+    times = np.asarray(times)
+    if rezero_to_first_event:
+        times = (times - times[0]).astype(np.float64)
+    else:
+        times = times.astype(np.float64)
+    length = times[-1]
+    if length < segment_size:
+        segment_size = length
+    start_times = np.arange(times[0], times[-1], segment_size)
+    masks = []
+    for s in start_times:
+        if drop_last_event:
+            good = (times >= s) & (times < s + segment_size)
+        else:
+            good = (times >= s) & (times <= s + segment_size)
+        ts = times[good]
+        if len(ts) < 1 or ts[-1] - ts[0] < 0.2 * segment_size:
+            continue
+        masks.append(good)
+    return times, masks
+
+
+@njit()
+def _stat_from_profile(prof, nharm, ctab, stab):
+    """nharm == 0: ef_profile_stat; else z_n_binned_events (stride-k table reads)."""
+    nbin = prof.size
+    if nharm == 0:
+        mean = 0.0
+        for j in range(nbin):
+            mean += prof[j]
+        mean /= nbin
+        chi = 0.0
+        for j in range(nbin):
+            d = prof[j] - mean
+            chi += d * d / mean
+        return chi
+    tot = 0.0
+    for j in range(nbin):
+        tot += prof[j]
+    res = 0.0
+    for k in range(1, nharm + 1):
+        c = 0.0
+        s = 0.0
+        for j in range(nbin):
+            idx = (j * k) % nbin
+            c += ctab[idx] * prof[j]
+            s += stab[idx] * prof[j]
+        res += c * c + s * s
+    return 2.0 / tot * res
+
+
+@njit()
+def _fold_one(ts, f, fd, nbin, prof):
+    """One trial: fused _pulse_phase_fast + _profile_fast (bit-identical arithmetic)."""
+    prof[:] = 0
+    for i in range(ts.size):
+        ph = ts[i] * f + 0.5 * ts[i] * ts[i] * fd
+        ph -= np.floor(ph)
+        b = np.int64(np.floor(ph * nbin))
+        if b >= nbin:
+            b = nbin - 1
+        if b < 0:
+            b = 0
+        prof[b] += 1
+
+
+@njit()
+def _search_serial(ts, freqs, fdots, nbin, nharm, ctab, stab, stats, profiles, want_profiles):
+    """The upstream hot loop: serial over fdots then freqs (Appendix A)."""
+    prof = np.zeros(nbin, dtype=np.int64)
+    for i in range(fdots.size):
+        for j in range(freqs.size):
+            _fold_one(ts, freqs[j], fdots[i], nbin, prof)
+            stats[i, j] += _stat_from_profile(prof, nharm, ctab, stab)
+            if want_profiles:
+                for b in range(nbin):
+                    profiles[i, j, b] += prof[b]
+
+
+@njit(parallel=True)
+def _search_parallel(ts, freqs, fdots, nbin, nharm, ctab, stab, stats):
+    """Same arithmetic, trials spread over host threads (CPU-baseline 'all cores' leg)."""
+    nf = freqs.size
+    ntr = fdots.size * nf
+    for g in prange(ntr):
+        i = g // nf
+        j = g - i * nf
+        prof = np.zeros(nbin, dtype=np.int64)
+        _fold_one(ts, freqs[j], fdots[i], nbin, prof)
+        stats[i, j] += _stat_from_profile(prof, nharm, ctab, stab)
+
+
+def _tables(nbin):
+    tw = np.pi * 2 * np.arange(nbin) * (1.0 / nbin)
+    return np.cos(tw), np.sin(tw)
+
+
+def folding_search_core(
+    times,
+    frequencies,
+    fdots=0,
+    nbin=128,
+    nharm=0,
+    segment_size=np.inf,
+    rezero_to_first_event=True,
+    drop_last_event=True,
+    return_profiles=False,
+    parallel=False,
+):
+    """Upstream ``_folding_search`` fast branch, for EF (nharm=0) or Z^2_n (nharm>=1).
+
+    Returns (fgrid, stats) when a single fdot is given, else (fgrid, fdgrid, stats) with
+    shape (n_fdot, n_freq).  With ``return_profiles`` the int64 profiles summed over
+    segments, shape (n_fdot, n_freq, nbin), are appended."""
+    frequencies = np.atleast_1d(np.asarray(frequencies, dtype=np.float64))
+    fdots = np.atleast_1d(np.asarray(fdots, dtype=np.float64))
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    stats = np.zeros_like(fgrid)
+    profiles = np.zeros(fgrid.shape + (nbin,), dtype=np.int64) if return_profiles else np.zeros((1, 1, 1), dtype=np.int64)
+    times, masks = select_segments(times, segment_size, rezero_to_first_event, drop_last_event)
+    ctab, stab = _tables(nbin)
+    count = 0
+    for good in masks:
+        ts = np.ascontiguousarray(times[good])
+        if parallel and not return_profiles:
+            _search_parallel(ts, frequencies, fdots, nbin, nharm, ctab, stab, stats)
+        else:
+            _search_serial(ts, frequencies, fdots, nbin, nharm, ctab, stab, stats, profiles, return_profiles)
+        count += 1
+    if count > 0:
+        stats = stats / count
+    if fgrid.shape[0] == 1:
+        out = (fgrid.flatten(), stats.flatten())
+    else:
+        out = (fgrid, fdgrid, stats)
+    if return_profiles:
+        out = out + (profiles,)
+    return out
+
+
+def epoch_folding_search(times, frequencies, nbin=128, segment_size=np.inf, expocorr=False, gti=None, weights=1, fdots=0, **kw):
+    """stingray.pulse.search.epoch_folding_search (fast branch only)."""
+    if expocorr and gti is None:
+        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    return folding_search_core(times, frequencies, fdots=fdots, nbin=nbin, nharm=0, segment_size=segment_size, **kw)
+
+
+def z_n_search(times, frequencies, nharm=4, nbin=128, segment_size=np.inf, expocorr=False, weights=1, gti=None, fdots=0, **kw):
+    """stingray.pulse.search.z_n_search (fast, binned branch only)."""
+    if expocorr and gti is None:
+        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    return folding_search_core(times, frequencies, fdots=fdots, nbin=nbin, nharm=nharm, segment_size=segment_size, **kw)
+
+
+def folding_search(
+    event_times,
+    gti_start,
+    fmin,
+    fmax,
+    step=None,
+    func=epoch_folding_search,
+    oversample=2,
+    fdotmin=0,
+    fdotmax=0,
+    fdotstep=None,
+    **kwargs,
+):
+    """hendrics/efsearch.py:1141-1193 on plain arrays (events.time, events.gti[0, 0])."""
+    times = (np.asarray(event_times) - gti_start).astype(np.float64)
+    length = times[-1]
+    if step is None:
+        step = 1 / oversample / length
+    if fdotstep is None:
+        fdotstep = 1 / oversample / length**2
+    epsilon = 1e-8 * step
+    trial_freqs = np.arange(fmin, fmax + epsilon, step)
+    fdotepsilon = 1e-2 * fdotstep
+    trial_fdots = np.arange(fdotmin, fdotmax + fdotepsilon, fdotstep)
+    results = func(times, trial_freqs, fdots=trial_fdots, **kwargs)
+    if len(results) == 2:
+        frequencies, stats = results
+        return frequencies, stats, step, length
+    frequencies, fdots, stats = results
+    return frequencies, fdots, stats, step, fdotstep, length
+
+
+# --------------------------------------------------------------------------------------
+# --fast ("quasi-fast folding")
+# --------------------------------------------------------------------------------------
+ONE_SIXTH = 1 / 6
+
+
+def fast_phase(ts, mean_f):
+    """hendrics/efsearch.py:870-873."""
+    phases = ts * mean_f
+    return phases - np.floor(phases)
+
+
+def fast_phase_fdot(ts, mean_f, mean_fdot=0):
+    """hendrics/efsearch.py:854-857."""
+    phases = ts * mean_f + 0.5 * ts * ts * mean_fdot
+    return phases - np.floor(phases)
+
+
+def fast_phase_fddot(ts, mean_f, mean_fdot=0, mean_fddot=0):
+    """hendrics/efsearch.py:863-867."""
+    tssq = ts * ts
+    phases = ts * mean_f + 0.5 * tssq * mean_fdot + ONE_SIXTH * tssq * ts * mean_fddot
+    return phases - np.floor(phases)
+
+
+@njit()
+def _hist2d_seq(H, x, y, bins, ranges):
+    """hendrics/base.py:667-677 (right edges excluded, truncating index)."""
+    delta0 = 1 / ((ranges[0, 1] - ranges[0, 0]) / bins[0])
+    delta1 = 1 / ((ranges[1, 1] - ranges[1, 0]) / bins[1])
+    for t in range(x.size):
+        i = (x[t] - ranges[0, 0]) * delta0
+        j = (y[t] - ranges[1, 0]) * delta1
+        if 0 <= i < bins[0] and 0 <= j < bins[1]:
+            H[int(i), int(j)] += 1
+    return H
+
+
+def histogram2d(x, y, bins, range):
+    """hendrics/base.py:680-693, 913-945 (unweighted numba variant)."""
+    H = np.zeros((bins[0], bins[1]), dtype=np.uint64)
+    return _hist2d_seq(
+        H,
+        np.asarray(x, dtype=np.float64),
+        np.asarray(y, dtype=np.float64),
+        np.asarray(list(bins), dtype=np.int64),
+        np.asarray(range, dtype=np.float64),
+    )
+
+
+@njit()
+def shift_and_sum(repeated_profiles, lshift, qshift, splat_prof, base_shift, quadbaseshift):
+    """hendrics/efsearch.py:350-363."""
+    nprof = repeated_profiles.shape[0]
+    nbin = splat_prof.size
+    twonbin = nbin * 2
+    splat_prof[:] = 0.0
+    for k in range(nprof):
+        total_shift = base_shift[k] * lshift + quadbaseshift[k] * qshift
+        total_shift = np.mod(np.rint(total_shift), nbin)
+        total_shift_int = int(total_shift)
+        splat_prof[:] += repeated_profiles[k, nbin - total_shift_int : twonbin - total_shift_int]
+    return splat_prof
+
+
+@njit()
+def _fast_step_impl(profiles, L, Q, nbin, n, return_splats):
+    twopiphases = 2 * np.pi * np.arange(0, 1, 1 / nbin)
+    cached_cos = np.zeros(n * nbin)
+    cached_sin = np.zeros(n * nbin)
+    for i in range(n):
+        cached_cos[i * nbin : (i + 1) * nbin] = np.cos(twopiphases)
+        cached_sin[i * nbin : (i + 1) * nbin] = np.sin(twopiphases)
+    stats = np.zeros_like(L)
+    repeated_profiles = np.hstack((profiles, profiles, profiles))
+    nprof = repeated_profiles.shape[0]
+    base_shift = np.linspace(-1, 1, nprof)
+    quad_base_shift = base_shift**2
+    splats = np.zeros((L.shape[0] if return_splats else 1, L.shape[1] if return_splats else 1, nbin))
+    for i in range(L.shape[0]):
+        splat_prof = np.zeros(nbin)
+        for j in range(L.shape[1]):
+            splat_prof = shift_and_sum(repeated_profiles, L[i, j], Q[i, j], splat_prof, base_shift, quad_base_shift)
+            # note: reference passes (cos, sin) into the (sin, cos) slots -- symmetric (efsearch.py:848)
+            stats[i, j] = _z_n_fast_cached(splat_prof, cached_cos, cached_sin, n)
+            if return_splats:
+                splats[i, j, :] = splat_prof
+    return stats, splats
+
+
+def fast_step(profiles, L, Q, nbin, n=2, return_splats=False):
+    """hendrics/efsearch.py:817-851."""
+    stats, splats = _fast_step_impl(np.asarray(profiles, dtype=np.float64), L, Q, nbin, n, return_splats)
+    if return_splats:
+        return stats, splats
+    return stats
+
+
+def search_with_qffa_step(
+    times, mean_f, mean_fdot=0, mean_fddot=0, nbin=16, nprof=64, npfact=2, oversample=8, n=1, search_fdot=True, return_profiles=False
+):
+    """hendrics/efsearch.py:876-925."""
+    if mean_fddot != 0:
+        phases = fast_phase_fddot(times, mean_f, mean_fdot, mean_fddot)
+    elif mean_fdot != 0:
+        phases = fast_phase_fdot(times, mean_f, mean_fdot)
+    else:
+        phases = fast_phase(times, mean_f)
+    profiles = histogram2d(phases, times, range=[[0, 1], [times[0], times[-1]]], bins=(nbin, nprof)).T
+    t1, t0 = times[-1], times[0]
+    linbinshifts = np.linspace(-nbin * npfact, nbin * npfact, int(oversample * npfact))
+    if search_fdot:
+        quabinshifts = np.linspace(-nbin * npfact, nbin * npfact, int(oversample * npfact))
+    else:
+        quabinshifts = np.array([0])
+    dphi = 1 / nbin
+    delta_t = (t1 - t0) / 2
+    bin_to_frequency = dphi / delta_t
+    bin_to_fdot = 2 * dphi / delta_t**2
+    L, Q = np.meshgrid(linbinshifts, quabinshifts, indexing="ij")
+    stats = fast_step(profiles, L, Q, nbin, n=n)
+    out = (L * bin_to_frequency + mean_f, Q * bin_to_fdot + mean_fdot, stats)
+    if return_profiles:
+        out = out + (profiles,)
+    return out
+
+
+def check_phase_error_after_casting_to_double(tref, f, fdot=0, rng=None):
+    """hendrics/efsearch.py:199-205 (the reference draws from the unseeded global RNG)."""
+    rng = np.random if rng is None else rng
+    times = np.array(rng.normal(tref, 0.1, 1000), dtype=np.longdouble)
+    times_dbl = times.astype(np.double)
+    phase = times * f + 0.5 * times**2 * fdot
+    phase_dbl = times_dbl * np.double(f) + 0.5 * times_dbl**2 * np.double(fdot)
+    return np.max(np.abs(phase_dbl - phase))
+
+
+def qffa_centres(f0, f1, length, npfact=2, fdot=0, fddot=0):
+    """Centre (mean_f, mean_fdot, mean_fddot) list of hendrics/efsearch.py:1004-1032."""
+    frequency = (f0 + f1) / 2
+    step = 4 * npfact / length
+    niter = int(np.rint((f1 - f0) / step)) + 2
+    allvalues = list(range(-(niter // 2), niter // 2))
+    if allvalues == []:
+        allvalues = [0]
+    cents = []
+    for i in allvalues:
+        offset = step * i
+        cents.append((np.double(frequency + offset + 0.12 * step), np.double(fdot + 0), np.double(fddot)))
+    return cents, step
+
+
+def search_with_qffa(
+    times, f0, f1, fdot=0, fddot=0, nbin=16, nprof=None, npfact=2, oversample=8, n=1, search_fdot=True, t0=None, t1=None, **_ignored
+):
+    """hendrics/efsearch.py:928-1089 (in-memory result arrays)."""
+    if nprof is None:
+        nprof = 4 * 2 * nbin * npfact
+    times = copy.deepcopy(np.asarray(times))
+    if t0 is None:
+        t0 = times.min()
+    if t1 is None:
+        t1 = times.max()
+    meantime = (t1 + t0) / 2
+    times = times - meantime
+    maxerr = check_phase_error_after_casting_to_double(np.max(times), f1, fdot)
+    if maxerr > 1 / nbin / 10:
+        warnings.warn(f"Maximum error on the phase expected when casting to double: {maxerr}")
+    times = times.astype(np.double)
+    length = t1 - t0
+    cents, step = qffa_centres(f0, f1, length, npfact, fdot, fddot)
+    all_f, all_fd, all_s = [], [], []
+    for mean_f, mean_fdot, mean_fddot in cents:
+        fgrid, fdotgrid, stats = search_with_qffa_step(
+            times, mean_f, mean_fdot=mean_fdot, mean_fddot=mean_fddot, nbin=nbin, nprof=nprof, npfact=npfact,
+            oversample=oversample, n=n, search_fdot=search_fdot,
+        )
+        all_f.append(fgrid)
+        all_fd.append(fdotgrid)
+        all_s.append(stats)
+    all_fgrid = np.concatenate(all_f, axis=0)
+    all_fdotgrid = np.concatenate(all_fd, axis=0)
+    all_stats = np.concatenate(all_s, axis=0)
+    step = np.median(np.diff(all_fgrid[:, 0]))
+    fdotstep = np.median(np.diff(all_fdotgrid[0]))
+    if search_fdot:
+        return all_fgrid.T, all_fdotgrid.T, all_stats.T, step, fdotstep, length
+    return all_fgrid.T[0], all_stats.T[0], step, length
+
+
+# --------------------------------------------------------------------------------------
+# candidates
+# --------------------------------------------------------------------------------------
+def find_peaks_in_image(image, n=5):
+    """hendrics/base.py:1140-1146 (the branch taken when skimage is absent / rough=True)."""
+    image = np.asarray(image)
+    best_cands = [np.unravel_index(idx, image.shape) for idx in np.argpartition(image.flatten(), -n)[-n:]]
+    best_stats = [image[bci] for bci in best_cands]
+    return np.asarray(best_cands)[np.argsort(best_stats)][::-1]
+
+
+def topk_flat(stats, k):
+    """Deterministic top-k used for the 'identical candidate list' check: value descending,
+    ties broken by ascending flat index (last bullet)."""
+    flat = np.asarray(stats).ravel()
+    k = min(k, flat.size)
+    order = np.lexsort((np.arange(flat.size), -flat))[:k]
+    return order.astype(np.int64), flat[order]
+
+
+def search_best_peaks(x, stat, threshold):
+    """stingray.pulse.search.search_best_peaks [UPSTREAM-RECALLED]: contiguous regions with
+    stat >= threshold -> arg-max of each, sorted by stat descending."""
+    x = np.asarray(x)
+    stat = np.asarray(stat)
+    peaks = stat >= threshold
+    best_x, best_stat = [], []
+    i = 0
+    n = stat.size
+    while i < n:
+        if not peaks[i]:
+            i += 1
+            continue
+        j = i
+        while j < n and peaks[j]:
+            j += 1
+        m = i + int(np.argmax(stat[i:j]))
+        best_x.append(x[m])
+        best_stat.append(stat[m])
+        i = j
+    order = np.argsort(best_stat)[::-1]
+    return [best_x[o] for o in order], [best_stat[o] for o in order]
+
+
+# --------------------------------------------------------------------------------------
+# long-double reference for the "more accurate than the reference" fixed-point mode
+# --------------------------------------------------------------------------------------
+def exact_bins(ts, f, fd, nbin):
+    """floor(frac(t*f + 0.5*t^2*fd) * nbin) evaluated in exact rational arithmetic on the
+    fp64 inputs (Python ints via float.as_integer_ratio); used for bin-flip counts."""
+    from fractions import Fraction
+
+    F = Fraction(float(f))
+    FD = Fraction(float(fd))
+    out = np.empty(len(ts), dtype=np.int64)
+    for i, t in enumerate(ts):
+        T = Fraction(float(t))
+        ph = T * F + Fraction(1, 2) * T * T * FD
+        fr = ph - math.floor(ph)
+        out[i] = int(math.floor(fr * nbin))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# synthetic HENfake-style event lists (benchmark inputs) -- shared by tests/bench
+# --------------------------------------------------------------------------------------
+def simulate_events(n_events, tstop, f0=1 / 0.101, amp=0.25, seed=1, tstart=0.0):
+    """N sorted fp64 arrival times on [tstart, tstop) from rate ~ 1 + amp*cos(2 pi f0 t),
+    by thinning a uniform sample (recipe of tests/test_efsearch.py:46-62 restated)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(0)
+    while out.size < n_events:
+        m = int((n_events - out.size) * (1 + amp) * 1.05) + 16
+        t = rng.uniform(tstart, tstop, m)
+        keep = rng.uniform(0, 1 + amp, m) < 1 + amp * np.cos(2 * np.pi * f0 * t)
+        out = np.concatenate([out, t[keep]])
+    out = out[:n_events]
+    out.sort()
+    return out

@@ -1,0 +1,167 @@
+"""K1 parity: CUDA fold search vs the CPU oracle (profiles bit-exact, statistics rel 1e-9)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import hx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # north_star tolerance for Z^2_n / chi^2 in fp64
+
+
+def _events(n, T, seed):
+    return O.simulate_events(n, T, seed=seed)
+
+
+def _host_call(ts, freqs, fdots, nbin, nharm, flags=0, want_profiles=True):
+    from hendrics_b200 import _cabi
+
+    ts = _cabi.as_f64(ts)
+    freqs = _cabi.as_f64(np.atleast_1d(freqs))
+    fdots = _cabi.as_f64(np.atleast_1d(fdots))
+    stats = np.empty((fdots.size, freqs.size))
+    prof = np.empty((fdots.size, freqs.size, nbin), dtype=np.uint32) if want_profiles else None
+    rc = _cabi.lib().hx_fold_search(
+        _cabi.dptr(ts), ts.size, _cabi.dptr(freqs), freqs.size, _cabi.dptr(fdots), fdots.size, nbin, nharm, flags,
+        _cabi.dptr(stats), prof.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)) if want_profiles else None, 0)
+    _cabi.check(rc)
+    return stats, prof
+
+
+def _assert_stats(got, ref):
+    good = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), good)
+    np.testing.assert_allclose(got[good], ref[good], rtol=RTOL, atol=0)
+
+
+CASES = [
+    # n_ev, T, nbin, nharm, n_f, fdots
+    (20000, 1000.0, 128, 2, 300, [0.0]),
+    (20000, 1000.0, 16, 0, 500, [0.0]),
+    (33333, 1000.0, 64, 4, 257, [-2e-6, 0.0, 3e-6]),
+    (5001, 300.0, 32, 1, 70, [1e-5]),
+    (20000, 1000.0, 8, 0, 100, [0.0, 1e-6]),
+    (4097, 1000.0, 256, 3, 65, [0.0]),
+    (3000, 1000.0, 1024, 2, 33, [0.0, 2e-6]),
+]
+
+
+@pytest.mark.parametrize("n_ev,T,nbin,nharm,n_f,fdots", CASES)
+@pytest.mark.parametrize("flags", [0, 2])
+def test_fold_matches_oracle(n_ev, T, nbin, nharm, n_f, fdots, flags):
+    ts = _events(n_ev, T, seed=n_ev % 97)
+    freqs = 9.85 + 0.1 * np.arange(n_f) / n_f
+    ref_s, ref_p = C.fold_search(ts, freqs, fdots, nbin, nharm, want_profiles=True)
+    want_prof = flags == 2
+    got_s, got_p = _host_call(ts, freqs, fdots, nbin, nharm, flags=flags, want_profiles=want_prof)
+    if want_prof:
+        assert np.array_equal(got_p.astype(np.int64), ref_p), "profile counts must be bit-exact"
+    _assert_stats(got_s, ref_s)
+
+
+@pytest.mark.parametrize("nbin,nharm", [(10, 0), (100, 2), (48, 3), (7, 1)])
+def test_fold_non_power_of_two_nbin(nbin, nharm):
+    ts = _events(15000, 800.0, seed=3)
+    freqs = 9.8 + 0.2 * np.arange(130) / 130
+    fdots = [0.0, 1e-6]
+    ref_s, ref_p = C.fold_search(ts, freqs, fdots, nbin, nharm, want_profiles=True)
+    got_s, got_p = _host_call(ts, freqs, fdots, nbin, nharm)
+    assert np.array_equal(got_p.astype(np.int64), ref_p)
+    _assert_stats(got_s, ref_s)
+
+
+def test_forced_generic_equals_fast_path():
+    ts = _events(20000, 1000.0, seed=5)
+    freqs = 9.85 + 0.1 * np.arange(200) / 200
+    fdots = [0.0, 4e-6]
+    a_s, a_p = _host_call(ts, freqs, fdots, 64, 2, flags=0)
+    b_s, b_p = _host_call(ts, freqs, fdots, 64, 2, flags=1)
+    assert np.array_equal(a_p, b_p)
+    np.testing.assert_allclose(a_s, b_s, rtol=1e-12)
+
+
+def test_negative_fdot_negative_phase():
+    """Negative phases (generic path is selected by the range check)."""
+    ts = _events(8000, 500.0, seed=7)
+    freqs = np.array([0.001, 0.01, 0.5])
+    fdots = [-1e-3, -1e-5]
+    ref_s, ref_p = C.fold_search(ts, freqs, fdots, 32, 2, want_profiles=True)
+    got_s, got_p = _host_call(ts, freqs, fdots, 32, 2)
+    assert np.array_equal(got_p.astype(np.int64), ref_p)
+    _assert_stats(got_s, ref_s)
+
+
+def test_long_baseline_large_phase():
+    """T = 1e8 s, f ~ 10 Hz: |phase| ~ 1e9 cycles; bins must still be bit-exact."""
+    rng = np.random.default_rng(11)
+    ts = np.sort(rng.uniform(0, 1e8, 30000))
+    freqs = 9.9 + 5e-9 * np.arange(96)
+    ref_s, ref_p = C.fold_search(ts, freqs, [0.0, 1e-16], 128, 2, want_profiles=True)
+    got_s, got_p = _host_call(ts, freqs, [0.0, 1e-16], 128, 2)
+    assert np.array_equal(got_p.astype(np.int64), ref_p)
+    _assert_stats(got_s, ref_s)
+
+
+def test_event_tail_sizes():
+    """Ragged event counts around the tile size (512) and odd counts (16-byte bulk-copy tail)."""
+    freqs = 9.85 + 0.1 * np.arange(40) / 40
+    base = _events(3000, 100.0, seed=13)
+    for n in [1, 2, 3, 511, 512, 513, 1023, 1025, 2049]:
+        ts = base[:n]
+        for fdots in ([0.0], [1e-5]):
+            ref_s, ref_p = C.fold_search(ts, freqs, fdots, 16, 1, want_profiles=True)
+            got_s, got_p = _host_call(ts, freqs, fdots, 16, 1)
+            assert np.array_equal(got_p.astype(np.int64), ref_p), (n, fdots)
+            _assert_stats(got_s, ref_s)
+
+
+def test_python_api_matches_oracle_search():
+    from hendrics_b200 import epoch_folding_search, z_n_search
+
+    ts = _events(20000, 1000.0, seed=1) + 8e7  # NuSTAR-like MET offset, removed by re-zeroing
+    freqs = np.arange(9.85, 9.95, 0.0005)
+    f0, s0 = O.z_n_search(ts, freqs, nharm=2, nbin=128)
+    f1, s1 = z_n_search(ts, freqs, nharm=2, nbin=128)
+    assert np.array_equal(f0, f1)
+    np.testing.assert_allclose(s1, s0, rtol=RTOL)
+    fd = np.array([-1e-6, 0, 2e-6])
+    r0 = O.epoch_folding_search(ts, freqs, nbin=16, fdots=fd)
+    r1 = epoch_folding_search(ts, freqs, nbin=16, fdots=fd)
+    assert len(r1) == 3 and r1[2].shape == (3, freqs.size)
+    np.testing.assert_allclose(r1[2], r0[2], rtol=RTOL)
+    assert np.array_equal(r1[0], r0[0]) and np.array_equal(r1[1], r0[1])
+    # same top-k candidate list
+    assert np.array_equal(O.topk_flat(r1[2], 10)[0], O.topk_flat(r0[2], 10)[0])
+
+
+def test_segments():
+    from hendrics_b200 import z_n_search
+
+    ts = _events(30000, 1000.0, seed=2)
+    freqs = np.arange(9.85, 9.95, 0.002)
+    f0, s0 = O.z_n_search(ts, freqs, nharm=2, nbin=32, segment_size=300.0)
+    f1, s1 = z_n_search(ts, freqs, nharm=2, nbin=32, segment_size=300.0)
+    np.testing.assert_allclose(s1, s0, rtol=RTOL)
+
+
+def test_many_trials_fused_path():
+    """Enough trials that the fused-epilogue (no scratch) path is taken, incl. a ragged last block."""
+    ts = _events(6000, 500.0, seed=4)
+    freqs = 5.0 + 10.0 * np.arange(40013) / 40013
+    fdots = [0.0, 1e-6, 2e-6]
+    ref = C.fold_search(ts, freqs, fdots, 16, 2)
+    got, _ = _host_call(ts, freqs, fdots, 16, 2, want_profiles=False)
+    _assert_stats(got, ref)
+    ref = C.fold_search(ts, freqs[:20011], [0.0], 128, 0)
+    got, _ = _host_call(ts, freqs[:20011], [0.0], 128, 0, want_profiles=False)
+    _assert_stats(got, ref)
+
+
+def test_microbench_runs():
+    from hendrics_b200 import _cabi
+
+    for kind in range(4):
+        assert _cabi.microbench(kind, reps=2) > 1e9
