@@ -13,9 +13,9 @@
  *     thread-local human-readable message for the last failure;
  *   - functions without a `_dev` suffix take HOST pointers and perform H2D copy, kernels and D2H
  *     copy synchronously on `device`;
- *   - `_dev` functions take DEVICE pointers (resident on the current device of `stream`), only
- *     enqueue work on `stream` (a cudaStream_t cast to void*, NULL = default stream) and do not
- *     synchronize, except where stated;
+ *   - `_dev` functions take DEVICE pointers for the bulk data (resident on the current device),
+ *     run on `stream` (a cudaStream_t cast to void*, NULL = default stream) and may synchronize
+ *     that stream before returning (they read back a few bytes of status);
  *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
  *     HX_ERR_CUDA.
  */
@@ -92,9 +92,12 @@ int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, co
                    const double *mean_fdd, int64_t n_centres, int nbin, int nprof, const double *L, const double *Q,
                    int64_t n_lq, int nharm, double *stats, uint32_t *profiles, int device);
 
-int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last, const double *d_mean_f,
-                       const double *d_mean_fd, const double *d_mean_fdd, int64_t n_centres, int nbin, int nprof,
-                       const double *d_L, const double *d_Q, int64_t n_lq, int nharm, double *d_stats,
+/* Device variant: only the event times and the outputs are device pointers; the per-centre
+ * scalars and the shift grids are small HOST arrays.  t_first/t_last are times_c[0] and
+ * times_c[n_ev-1] (the histogram range of efsearch.py:902).  Synchronizes `stream`. */
+int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last, const double *mean_f,
+                       const double *mean_fd, const double *mean_fdd, int64_t n_centres, int nbin, int nprof,
+                       const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
                        uint32_t *d_profiles, void *stream);
 
 /* ---- K4: unbinned Z^2_n (extension; oracle formula hendrics/efsearch.py:366-404) ---------
@@ -124,6 +127,10 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  * Runs on `device`, blocks, returns the best of `reps` timings.
  */
 int hx_microbench(int kind, int reps, double *ops_per_s, int device);
+
+/* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
+int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
+int hx_qffa_set_tuning(int centres_per_pass);
 
 #ifdef __cplusplus
 }

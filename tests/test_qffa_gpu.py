@@ -1,0 +1,103 @@
+"""K2/K3 parity: `--fast` 2-D profiles bit-exact, statistics rel 1e-9 vs the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import hx_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _centred(n, T, seed):
+    ts = O.simulate_events(n, T, seed=seed)
+    return ts - (ts.max() + ts.min()) / 2
+
+
+def _host_qffa(ts, cents, nbin, nprof, L, Q, n):
+    from hendrics_b200 import _cabi
+
+    ts = _cabi.as_f64(ts)
+    cents = np.asarray(cents, dtype=np.float64).reshape(-1, 3)
+    mf, mfd, mfdd = (np.ascontiguousarray(cents[:, i]) for i in range(3))
+    Lf, Qf = _cabi.as_f64(L.ravel()), _cabi.as_f64(Q.ravel())
+    stats = np.empty((cents.shape[0], Lf.size))
+    prof = np.empty((cents.shape[0], nprof, nbin), dtype=np.uint32)
+    rc = _cabi.lib().hx_qffa_search(
+        _cabi.dptr(ts), ts.size, _cabi.dptr(mf), _cabi.dptr(mfd), _cabi.dptr(mfdd), cents.shape[0], nbin, nprof,
+        _cabi.dptr(Lf), _cabi.dptr(Qf), Lf.size, n, _cabi.dptr(stats),
+        prof.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 0)
+    _cabi.check(rc)
+    return stats.reshape((cents.shape[0],) + L.shape), prof
+
+
+@pytest.mark.parametrize("nbin,nprof,n,mode", [(16, 128, 1, 0), (32, 64, 2, 1), (128, 2048, 2, 0), (64, 100, 3, 2),
+                                               (10, 37, 1, 1)])
+def test_qffa_step_matches_oracle(nbin, nprof, n, mode):
+    ts = _centred(40000, 2000.0, seed=nbin)
+    cents = []
+    for i in range(11):  # more than one fused group of centres
+        f = 9.88 + 0.004 * i
+        fd = 0.0 if mode == 0 else 1e-7 * (i - 3)
+        fdd = 0.0 if mode < 2 else 1e-11 * (i + 1)
+        cents.append((f, fd, fdd))
+    lin = np.linspace(-nbin * 2, nbin * 2, 16)
+    L, Q = np.meshgrid(lin, lin, indexing="ij")
+    stats, prof = _host_qffa(ts, cents, nbin, nprof, L, Q, n)
+    for ic, (f, fd, fdd) in enumerate(cents):
+        ref_p = C.qffa_profiles(ts, f, fd, fdd, nbin, nprof)
+        assert np.array_equal(prof[ic].astype(np.uint64), ref_p), f"centre {ic}: 2-D profile not bit-exact"
+        ref_s = C.fast_step(ref_p, L, Q, n)
+        np.testing.assert_allclose(stats[ic], ref_s, rtol=RTOL)
+    # the python oracle agrees with the C oracle on the first centre (numba path of the reference)
+    f, fd, fdd = cents[0]
+    py = O.search_with_qffa_step(ts, f, fd, fdd, nbin=nbin, nprof=nprof, npfact=2, oversample=8, n=n,
+                                 return_profiles=True)
+    assert np.array_equal(py[3], prof[0].astype(np.uint64))
+    np.testing.assert_allclose(stats[0], py[2], rtol=RTOL)
+
+
+def test_qffa_last_event_dropped_and_gaps():
+    """Right edge excluded (base.py:674) and a long data gap (rows outside the smem window)."""
+    rng = np.random.default_rng(3)
+    ts = np.sort(np.concatenate([rng.uniform(0, 100, 9000), rng.uniform(5000, 5100, 9000)]))
+    ts = ts - (ts.max() + ts.min()) / 2
+    lin = np.linspace(-32, 32, 8)
+    L, Q = np.meshgrid(lin, lin, indexing="ij")
+    stats, prof = _host_qffa(ts, [(3.3, 0, 0)], 16, 128, L, Q, 2)
+    ref_p = C.qffa_profiles(ts, 3.3, 0, 0, 16, 128)
+    assert np.array_equal(prof[0].astype(np.uint64), ref_p)
+    assert prof[0].sum() == ts.size - 1  # t == t[-1] is not counted
+    np.testing.assert_allclose(stats[0], C.fast_step(ref_p, L, Q, 2), rtol=RTOL)
+
+
+def test_search_with_qffa_api():
+    from hendrics_b200.efsearch import search_with_qffa, search_with_qffa_step
+
+    ts = O.simulate_events(30000, 1000.0, seed=9) + 8e7
+    np.random.seed(0)
+    ref = O.search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, oversample=8)
+    got = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, oversample=8, silent=True)
+    assert len(got) == 6
+    for a, b in zip(got[:2], ref[:2]):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(got[2], ref[2], rtol=RTOL)
+    assert got[3] == ref[3] and got[4] == ref[4] and got[5] == ref[5]
+    # best candidate close to the injected pulse
+    i = np.unravel_index(np.argmax(got[2]), got[2].shape)
+    assert abs(got[0][i] - 1 / 0.101) < 2 / 1000.0
+    # no fdot search -> 4-tuple of 1-D arrays
+    ref4 = O.search_with_qffa(ts, 9.85, 9.95, nbin=16, n=1, search_fdot=False)
+    got4 = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=1, search_fdot=False)
+    assert len(got4) == 4 and got4[0].ndim == 1
+    assert np.array_equal(got4[0], ref4[0])
+    np.testing.assert_allclose(got4[1], ref4[1], rtol=RTOL)
+    # single step API
+    tc = (ts - (ts.max() + ts.min()) / 2).astype(np.float64)
+    r = O.search_with_qffa_step(tc, 9.9, nbin=16, nprof=128, n=2, return_profiles=True)
+    g = search_with_qffa_step(tc, 9.9, nbin=16, nprof=128, n=2, return_profiles=True)
+    assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1])
+    assert np.array_equal(g[3].astype(np.uint64), r[3])
+    np.testing.assert_allclose(g[2], r[2], rtol=RTOL)
