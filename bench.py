@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the HENDRICS periodicity-search hot path on B200 ("Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c5] [--impl reference]
+
+One "step" = one pass of the search over this rank's slice of the trial grid on a synthetic
+HENfake-style event list.  Default workload = BASELINE.json configs[1] (C2: HENefsearch, epoch
+folding nbin=16, 1e6 events x 1e6 trial frequencies per GPU; the frequency grid is sharded over
+ranks -- weak scaling -- and the statistic slices are all-gathered once per step).
+
+Prints ONE JSON line (rank 0).  `value` = event*trials/s with inputs resident in HBM (CUDA events);
+`e2e` = the same metric through the public API `hendrics_b200.epoch_folding_search` / `z_n_search`
+from host arrays (H2D + kernels + D2H inside the timed region); `roofline` = K1 fold kernel against
+the FP64-pipe issue rate measured in the same process; `cpu_baseline` = the oracle port on this
+box's host cores.  `--impl reference` times only that CPU port.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Z_n^2 / epoch-folding search throughput (event*trials/s)"
+UNIT = "event*trials/s"
+
+# name -> (description, n_events, T, n_freq per GPU, f_start, f_step, n_fdot, fdot0, fdot_step, nbin, nharm, seed)
+WORKLOADS = {
+    "c1": ("C1: HENzsearch Z^2_2, 1e5 events x 1e4 trial frequencies, nbin=128, no fdot",
+           100_000, 1e5, 10_000, 9.876, 5e-6, 1, 0.0, 0.0, 128, 2, 1),
+    "c2": ("C2: HENefsearch epoch folding nbin=16, 1e6 events x 1e6 trial frequencies",
+           1_000_000, 1e5, 1_000_000, 7.4, 5e-6, 1, 0.0, 0.0, 16, 0, 2),
+    "c3": ("C3 slice: Z^2_4 nbin=128, 1e7 events x 2048 frequencies x 64 fdots per GPU "
+           "(full config: 1e6 frequencies sharded over 8 GPUs)",
+           10_000_000, 1e5, 2048, 7.4, 5e-6, 64, -1.6e-9, 5e-11, 128, 4, 3),
+    "c5": ("C5 slice: Z^2_2 nbin=128, long baseline 1e8 s, 2e7 events x 4096 frequencies per GPU",
+           20_000_000, 1e8, 4096, 9.9009, 5e-9, 1, 0.0, 0.0, 128, 2, 5),
+}
+
+
+def algorithmic_ops_per_evtr(n_fd_nonzero):
+    """6 FP64 ops per event*trial with fdot, 4 without (each op counts 1, no FMA)."""
+    return 6.0 if n_fd_nonzero else 4.0
+
+
+def make_inputs(wl, rank, world):
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, n_f, f0, fstep, n_fd, fd0, fdstep, nbin, nharm, seed = WORKLOADS[wl]
+    times = simulate_events(n_ev, T, seed=seed)  # identical on every rank (replicated event list)
+    lo = rank * n_f  # contiguous frequency slice of the (world * n_f)-wide grid
+    freqs = f0 + fstep * (lo + np.arange(n_f, dtype=np.float64))
+    fdots = fd0 + fdstep * np.arange(n_fd, dtype=np.float64) if n_fd > 1 else np.zeros(1)
+    return desc, times, freqs, fdots, nbin, nharm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def cpu_port_throughput(times, freqs, fdots, nbin, nharm, target_s=12.0):
+    """The oracle's C port (oracle/hx_oracle.c, all host threads) on a bounded sample of the same
+    workload: all events x the first S trial frequencies.  Returns (event*trials/s, cores, sample)."""
+    from oracle import c_oracle as C
+
+    cores = C.max_threads()
+    n_ev = times.size
+    ts = (times - times[0]).astype(np.float64)
+    ts = ts[ts < ts[-1]]
+    s = max(cores * 4, 8)
+    t0 = time.perf_counter()
+    C.fold_search(ts, freqs[:s], fdots[:1], nbin, nharm)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rate = ts.size * s / dt
+    n_tr = int(min(freqs.size * fdots.size, max(s, target_s * rate / ts.size)))
+    n_fd = min(fdots.size, max(1, n_tr // freqs.size)) if n_tr > freqs.size else 1
+    n_f = min(freqs.size, max(1, n_tr // n_fd))
+    t0 = time.perf_counter()
+    C.fold_search(ts, freqs[:n_f], fdots[:n_fd], nbin, nharm)
+    dt = time.perf_counter() - t0
+    sample = (f"oracle C port (pthreads, {cores} threads), {ts.size} events x {n_f} freqs x {n_fd} fdots "
+              f"of the workload, {dt:.1f} s")
+    return ts.size * n_f * n_fd / dt, cores, sample
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference's CPU algorithm (restated oracle; stingray itself is not
+    installable here) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, times, freqs, fdots, nbin, nharm = make_inputs(wl, 0, 1)
+    from oracle import c_oracle as C
+
+    cores = C.max_threads()
+    ts = (times - times[0]).astype(np.float64)
+    ts = ts[ts < ts[-1]]
+    # calibrate a ~2 s step
+    s = max(cores * 4, 8)
+    t0 = time.perf_counter()
+    C.fold_search(ts, freqs[:s], fdots[:1], nbin, nharm)
+    rate = ts.size * s / max(time.perf_counter() - t0, 1e-4)
+    n_fd = fdots.size if fdots.size > 1 else 1
+    n_f = int(min(freqs.size, max(cores, 2.0 * rate / ts.size / n_fd)))
+    for _ in range(args.warmup):
+        C.fold_search(ts, freqs[:n_f], fdots[:n_fd], nbin, nharm)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        C.fold_search(ts, freqs[:n_f], fdots[:n_fd], nbin, nharm)
+    dt = time.perf_counter() - t0
+    value = ts.size * n_f * n_fd * args.steps / dt
+    sample = f"per step: {ts.size} events x {n_f} freqs x {n_fd} fdots (bounded sample of the workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(ts.size),
+                   "n_freq_per_gpu": int(freqs.size), "n_fdot": int(fdots.size)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from hendrics_b200 import _cabi, epoch_folding_search, z_n_search
+    from hendrics_b200.search import fold_stats_device
+
+    desc, times, freqs, fdots, nbin, nharm = make_inputs(wl, rank, world)
+    has_fd = bool(np.any(fdots != 0))
+    dev = torch.device("cuda", local_rank)
+    # event selection of the public API (A1/A2), done once: resident inputs for the `value` leg
+    ts_host = (times - times[0]).astype(np.float64)
+    ts_host = ts_host[ts_host < ts_host[-1]]
+    ts_d = torch.from_numpy(ts_host).to(dev)
+    f_d = torch.from_numpy(freqs).to(dev)
+    fd_d = torch.from_numpy(fdots).to(dev)
+    n_tr_local = freqs.size * fdots.size
+    units_local = float(ts_host.size) * n_tr_local
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = [torch.empty((fdots.size, freqs.size), dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step_resident():
+        stats = fold_stats_device(ts_d, f_d, fd_d, nbin, nharm)
+        if world > 1:
+            dist.all_gather(gathered, stats)  # the one data-path collective: statistic slices
+        return stats
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # evict the events from L2 between timed iterations (outside the timed interval)
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+        kern_ms.append(_cabi.fold_last_kernel()[0])
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = units_local * world * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    kms, grid, block, smem = _cabi.fold_last_kernel()
+    kern_avg_ms = float(np.mean(kern_ms))
+
+    # ---- e2e: public API, host arrays in, host arrays out --------------------------------------
+    pin_t = torch.from_numpy(times).pin_memory()
+    pin_f = torch.from_numpy(freqs).pin_memory()
+    t_np, f_np = pin_t.numpy(), pin_f.numpy()
+
+    def step_e2e():
+        if nharm == 0:
+            res = epoch_folding_search(t_np, f_np, nbin=nbin, fdots=fdots)
+        else:
+            res = z_n_search(t_np, f_np, nharm=nharm, nbin=nbin, fdots=fdots)
+        stats = res[-1]
+        if world > 1:
+            from hendrics_b200 import dist as hdist
+            stats = hdist.all_gather_concat(stats, [freqs.size] * world, axis=-1)
+        return stats
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tq = time.perf_counter()
+        step_e2e()
+        if os.environ.get("HX_BENCH_DEBUG"):
+            print(f"[debug] e2e step wall {time.perf_counter() - tq:.4f} s, kernel {_cabi.fold_last_kernel()}", file=sys.stderr)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_local * world * args.steps / float(e2e_s.item())
+    h2d = times.nbytes + freqs.nbytes + fdots.nbytes
+    d2h = n_tr_local * 8
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (K1 fold_kernel) ----------------------------------
+        peak_ops = _cabi.microbench(1, reps=5, device=local_rank)  # DMUL+DADD issue rate, inst/s
+        alg_ops = algorithmic_ops_per_evtr(has_fd) * units_local
+        achieved = alg_ops / (kern_avg_ms * 1e-3)
+        exec_ops = (4.0 if has_fd else 2.0) * units_local / (kern_avg_ms * 1e-3)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", f"fold_{wl}_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_gbs = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        roofline = {
+            "bound": "fp64_pipe", "achieved": achieved * 1e-12, "peak": peak_ops * 1e-12, "unit": "TFLOP/s",
+            "frac": achieved / peak_ops, "traffic": traffic,
+            "kernel": "hx::fold_kernel", "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
+            "algorithmic_fp64_ops_per_event_trial": algorithmic_ops_per_evtr(has_fd),
+            "executed_fp64_frac": exec_ops / peak_ops,
+            "peak_source": "measured in this process: hx_microbench kind 1 (DMUL+DADD issue rate, non-FMA op/s); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "hbm_peak_gbs": hbm_gbs, "hbm_peak_source": "measured" if os.path.exists(peaks_file) else "fallback",
+            "launch": {"grid": grid, "block": block, "dyn_smem_bytes": smem},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, sample = cpu_port_throughput(times, freqs, fdots, nbin, nharm)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(ts_host.size),
+                       "n_freq_per_gpu": int(freqs.size), "n_fdot": int(fdots.size),
+                       "parallelism": f"trial-grid sharding x{world}, events replicated, one all-gather of stats",
+                       "l2": "flushed between timed iterations (256 MiB write)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

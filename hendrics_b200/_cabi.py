@@ -41,6 +41,7 @@ SIGNATURES = {
     "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
     "hx_microbench": (_int, [_int, _int, _c_dp, _int]),
+    "hx_fold_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
     "hx_fold_set_tuning": (_int, [_int, _int]),
     "hx_qffa_set_tuning": (_int, [_int]),
 }
@@ -113,6 +114,13 @@ def device_count():
 
 def launch_count():
     return int(lib().hx_launch_count())
+
+
+def fold_last_kernel():
+    """(ms, grid, block, smem_bytes) of the most recent K1 launch."""
+    ms, g, b, s = _dbl(0.0), _i64(0), _i64(0), _i64(0)
+    check(lib().hx_fold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+    return ms.value, g.value, b.value, s.value
 
 
 def microbench(kind, reps=5, device=0):

@@ -52,6 +52,15 @@ int get_device_info(int device, DeviceInfo *out) {
         int cur = 0;
         HX_CUDA_TRY(cudaGetDevice(&cur));
         HX_CUDA_TRY(cudaSetDevice(device));
+        {
+            // keep stream-ordered temporaries (cudaMallocAsync) cached across calls: by default the
+            // pool hands memory back to the OS at every synchronisation point
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        }
         uint32_t *d = nullptr;
         HX_CUDA_TRY(cudaMalloc(&d, sizeof(uint32_t)));
         probe_smem_base_kernel<<<1, 32, 64>>>(d);

@@ -383,6 +383,12 @@ static fold_fn_t pick_fold(int R, bool has_fd, bool pow2) {
     }
 }
 
+// CUDA events bracketing the last fold_kernel launch (bench.py's live roofline measurement)
+static cudaEvent_t g_ev0[64], g_ev1[64];
+static bool g_ev_ok[64] = {false};
+static int g_last_timed_device = -1;
+static long long g_last_grid = 0, g_last_block = 0, g_last_smem = 0;
+
 static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
 
@@ -549,8 +555,17 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     fold_fn_t fn = pick_fold(R, has_fd, pow2);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem_bytes));
     dim3 grid((unsigned)n_cta_x, (unsigned)ev_splits);
+    if (!g_ev_ok[device]) {
+        HX_CUDA_TRY(cudaEventCreate(&g_ev0[device]));
+        HX_CUDA_TRY(cudaEventCreate(&g_ev1[device]));
+        g_ev_ok[device] = true;
+    }
+    HX_CUDA_TRY(cudaEventRecord(g_ev0[device], st));
     fn<<<grid, W * 32, best.smem_bytes, st>>>(a);
     HX_CHECK_LAUNCH("fold_kernel");
+    HX_CUDA_TRY(cudaEventRecord(g_ev1[device], st));
+    g_last_timed_device = device;
+    g_last_grid = (long long)n_cta_x * ev_splits, g_last_block = W * 32, g_last_smem = best.smem_bytes;
     if (!fused) {
         fold_stat_kernel<<<(unsigned)((n_trials + 255) / 256), 256, 2 * nbin * sizeof(double), st>>>(
             reinterpret_cast<uint32_t *>(d_scratch), n_trials, nbin, nharm, reinterpret_cast<double *>(d_tab), d_stats,
@@ -570,6 +585,22 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
 }  // namespace hx
 
 extern "C" {
+
+int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *smem_bytes) {
+    if (!ms || hx::g_last_timed_device < 0) {
+        hx::set_error("hx_fold_last_kernel_ms: no fold kernel has been launched");
+        return HX_ERR_ARG;
+    }
+    const int d = hx::g_last_timed_device;
+    float f = 0.f;
+    HX_CUDA_TRY(cudaEventSynchronize(hx::g_ev1[d]));
+    HX_CUDA_TRY(cudaEventElapsedTime(&f, hx::g_ev0[d], hx::g_ev1[d]));
+    *ms = f;
+    if (grid) *grid = hx::g_last_grid;
+    if (block) *block = hx::g_last_block;
+    if (smem_bytes) *smem_bytes = hx::g_last_smem;
+    return HX_OK;
+}
 
 int hx_fold_set_tuning(int R, int W) {
     hx::g_fold_R_override = (R == 1 || R == 2 || R == 4) ? R : 0;

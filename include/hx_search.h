@@ -128,6 +128,10 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  */
 int hx_microbench(int kind, int reps, double *ops_per_s, int device);
 
+/* Device time (CUDA events on the launching stream) and launch shape of the most recent K1
+ * fold_kernel launch of this process. */
+int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *smem_bytes);
+
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);
