@@ -8,13 +8,16 @@
 //   * lane = trial.  Every thread owns R trials and, for each, a PRIVATE nbin-bin uint32 histogram
 //     column in shared memory laid out [bin][lane] (word address = bin*32 + lane), so that every
 //     histogram access of a warp hits 32 distinct banks: no atomics, no bank conflicts.
-//   * events stream HBM/L2 -> shared memory through a 2-stage cp.async.bulk (TMA engine) + mbarrier
-//     pipeline and are broadcast to all threads with one LDS.128 per event (pair).
-//   * phase arithmetic is the reference's, rounding for rounding: t*f and q*fd (q = (0.5*t)*t) are
-//     separately rounded products, added with one rounding -- never an FMA.  For power-of-two nbin the
-//     trial constants are pre-scaled by nbin*128 (exact), floor() is one round-down add of 1.5*2^52
-//     and the bin byte offset is one AND of the low mantissa word; it is OR-ed into the (aligned)
-//     column base.  Per event*trial: 2 DMUL + 2 DADD + LOP3 + ATOMS (f only: DMUL + DADD + LOP3 + ATOMS).
+//   * event times (8 B each, nothing else) stream HBM/L2 -> shared memory through a 2-stage
+//     cp.async.bulk (TMA engine) + mbarrier pipeline and are broadcast to all threads, two events per
+//     LDS.128.  There is no block-wide barrier in the loop: the last warp to finish a stage refills it.
+//   * phase arithmetic is the reference's, rounding for rounding: t*f and (0.5*t*t)*fd are separately
+//     rounded products, added with one rounding -- never an FMA.  (0.5*t*t)*fd is evaluated as
+//     fl(t*t) * (0.5*fd): scaling by 0.5 is exact, so both orders round the same real number.  For
+//     power-of-two nbin the trial constants are pre-scaled by nbin*128 (exact), floor() is one
+//     round-down add of 1.5*2^52 and the bin byte offset is one AND of the low mantissa word; it is
+//     OR-ed into the (aligned) column base.  Per event*trial: 2 DMUL + 2 DADD + LOP3 + ATOMS, plus one
+//     DMUL (t*t) per event per thread amortised over its R trials (f only: DMUL + DADD + LOP3 + ATOMS).
 //   * the increment is a fire-and-forget `red.shared.add.u32` on the thread's private column
 //     (measured on B200: 26 conflict-free lanes/clk/SM vs 15.8 for LDS+IADD+STS, one issue slot
 //     instead of three and no load->add->store dependency chain); the next group of events is
@@ -31,11 +34,12 @@
 
 namespace hx {
 
-constexpr int TILE_EV = 512;  // events per pipeline stage
-constexpr int TILE_PAD = 8;   // events of slack after each stage (register prefetch may read past cnt)
+constexpr int TILE_EV_MAX = 1024;  // events per pipeline stage (runtime: 256..1024, multiple of 64)
+constexpr int TILE_PAD = 8;        // events of slack after each stage (register prefetch may read past cnt)
+constexpr uint32_t SMEM_HDR = 32;  // two mbarriers + two "warps done" counters
 
 struct FoldArgs {
-    const double *ev;  // HAS_FD ? interleaved (t, q) : t
+    const double *ev;  // event times
     long long n_ev;
     const double *freqs;
     long long n_f;
@@ -44,6 +48,7 @@ struct FoldArgs {
     int nbin;
     int nharm;
     uint32_t binmask;  // POW2: (nbin-1) << 7
+    int tile_ev;       // events per pipeline stage
     double scale;      // POW2: nbin*128, generic: 1
     double *stats;
     uint32_t *scratch;  // null => fused epilogue
@@ -54,11 +59,12 @@ struct FoldArgs {
     int *errflag;
 };
 
+// tt = fl(t*t); fdH = 0.5*fd*scale (exact scalings), so fl(tt*fdH) == scale * fl(((0.5*t)*t)*fd)
 template <bool HAS_FD, bool POW2>
-__device__ __forceinline__ uint32_t bin_addr(double t, double q, double fN, double fdN, uint32_t mask, int nbin,
+__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double fN, double fdH, uint32_t mask, int nbin,
                                              uint32_t cb) {
     double x = __dmul_rn(t, fN);
-    if (HAS_FD) x = __dadd_rn(x, __dmul_rn(q, fdN));
+    if (HAS_FD) x = __dadd_rn(x, __dmul_rn(tt, fdH));
     if (POW2) {
         // x = nbin*128*phase exactly; floor -> low word; bits [7, 7+log2 nbin) are the bin
         double y = __dadd_rd(x, HX_MAGIC);
@@ -110,35 +116,39 @@ __device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const
 
 template <bool HAS_FD, int UE>
 struct EvGroup {
-    double t[UE], q[UE];
+    double t[UE], tt[UE];
     __device__ __forceinline__ void load(const unsigned char *tp, int e) {
-        if (HAS_FD) {
 #pragma unroll
-            for (int u = 0; u < UE; u++) {
-                double2 v = *reinterpret_cast<const double2 *>(tp + (size_t)(e + u) * 16);
-                t[u] = v.x, q[u] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < UE; u += 2) {
-                double2 v = *reinterpret_cast<const double2 *>(tp + (size_t)(e + u) * 8);
-                t[u] = v.x, t[u + 1] = v.y, q[u] = 0.0, q[u + 1] = 0.0;
-            }
+        for (int u = 0; u < UE; u += 2) {
+            double2 v = *reinterpret_cast<const double2 *>(tp + (size_t)(e + u) * 8);
+            t[u] = v.x, t[u + 1] = v.y;
         }
+    }
+    __device__ __forceinline__ void squares() {
+#pragma unroll
+        for (int u = 0; u < UE; u++) tt[u] = HAS_FD ? __dmul_rn(t[u], t[u]) : 0.0;
     }
 };
 
+// events per register group: enough independent DMUL->DADD->DADD.RM->LOP3->ATOMS chains per warp
+// (R*UE) to cover the FP64 latency with the few warps the histograms leave room for
+template <int R, bool HAS_FD>
+struct GroupSize {
+    static constexpr int value = HAS_FD ? (R >= 8 ? 2 : R >= 4 ? 4 : 8) : (R >= 4 ? 2 : 4);
+};
+
 template <int R, bool HAS_FD, bool POW2>
-__global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
+__global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int UE = (R >= 4) ? 2 : 4;  // events per register group
+    constexpr int UE = GroupSize<R, HAS_FD>::value;
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t blk = (uint32_t)a.nbin << 7;  // bytes of one (warp, r) histogram block
     const uint32_t hist = sbase + a.hist_off;
     const uint32_t tileb = sbase + a.tile_off;
-    constexpr int EVB = HAS_FD ? 16 : 8;
-    constexpr uint32_t TILE_BYTES = (TILE_EV + TILE_PAD) * EVB;
+    const int TILE_EV = a.tile_ev;
+    const uint32_t TILE_BYTES = (uint32_t)(TILE_EV + TILE_PAD) * 8u;
+    int *done = reinterpret_cast<int *>(smem + 16);  // [2] warps that finished the stage
 
     if (POW2 && (hist & (blk - 1)) != 0) {  // host/device layout disagreement: refuse to compute
         if (tid == 0) atomicExch(a.errflag, 1);
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
 
     // trial constants
     const long long tb = (long long)blockIdx.x * a.warps + warp;  // block of 32*R trials
-    double fN[R], fdN[R];
+    double fN[R], fdH[R];
     uint32_t cb[R];
     bool valid[R];
 #pragma unroll
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
         long long gi = valid[r] ? g : 0;
         long long ifd = gi / a.n_f, jf = gi - ifd * a.n_f;
         fN[r] = valid[r] ? __dmul_rn(a.freqs[jf], a.scale) : 0.0;
-        fdN[r] = (HAS_FD && valid[r]) ? __dmul_rn(a.fdots[ifd], a.scale) : 0.0;
+        fdH[r] = (HAS_FD && valid[r]) ? __dmul_rn(__dmul_rn(0.5, a.fdots[ifd]), a.scale) : 0.0;
         cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * 4u;
     }
 
@@ -176,24 +186,25 @@ __global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
     auto issue = [&](int it) {
         const long long s = e0 + (long long)it * TILE_EV;
         const int cnt = (int)min((long long)TILE_EV, e1 - s);
-        const uint32_t bytes = (uint32_t)cnt * EVB, bulk = bytes & ~15u;
+        const uint32_t bytes = (uint32_t)cnt * 8u, bulk = bytes & ~15u;
         const uint32_t dst = tileb + (uint32_t)(it & 1) * TILE_BYTES;
-        const char *src = reinterpret_cast<const char *>(a.ev) + s * EVB;
+        const char *src = reinterpret_cast<const char *>(a.ev) + s * 8;
+        if (bytes != bulk) {  // odd trailing fp64: plain copy, ordered before the arrive below
+            double v = *reinterpret_cast<const double *>(src + bulk);
+            *reinterpret_cast<double *>(smem + a.tile_off + (uint32_t)(it & 1) * TILE_BYTES + bulk) = v;
+        }
         if (bulk) {
             mbar_expect_tx(bar[it & 1], bulk);
             bulk_g2s(dst, src, bulk, bar[it & 1]);
         } else {
             mbar_arrive(bar[it & 1]);
         }
-        if (bytes != bulk) {  // odd trailing fp64 (t-only tiles): plain copy, published by the next barrier
-            double v = *reinterpret_cast<const double *>(src + bulk);
-            *reinterpret_cast<double *>(smem + a.tile_off + (uint32_t)(it & 1) * TILE_BYTES + bulk) = v;
-        }
     };
 
     if (tid == 0) {
         mbar_init(bar[0], 1);
         mbar_init(bar[1], 1);
+        done[0] = 0, done[1] = 0;
         fence_mbar_init();
         fence_proxy_async();
         if (ntiles > 0) issue(0);
@@ -203,6 +214,7 @@ __global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
 
     const uint32_t mask = a.binmask;
     const int nbin = a.nbin;
+    const int nwarps = a.warps;
 
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
@@ -215,29 +227,37 @@ __global__ void __launch_bounds__(512, 2) fold_kernel(const FoldArgs a) {
         cur.load(tp, 0);
         for (; e + UE <= cnt; e += UE) {
             nxt.load(tp, e + UE);  // may read the pad after the stage; never used past cnt
+            cur.squares();
 #pragma unroll
             for (int u = 0; u < UE; u++) {
 #pragma unroll
                 for (int r = 0; r < R; r++)
-                    red_shared_inc(bin_addr<HAS_FD, POW2>(cur.t[u], cur.q[u], fN[r], fdN[r], mask, nbin, cb[r]));
-            }
-            cur = nxt;
-        }
-        for (; e < cnt; e++) {  // ragged end of the last stage
-            double t0, q0 = 0.0;
-            if (HAS_FD) {
-                double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)e * 16);
-                t0 = v0.x, q0 = v0.y;
-            } else {
-                t0 = *reinterpret_cast<const double *>(tp + (size_t)e * 8);
+                    red_shared_inc(bin_addr<HAS_FD, POW2>(cur.t[u], cur.tt[u], fN[r], fdH[r], mask, nbin, cb[r]));
             }
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                red_shared_inc(bin_addr<HAS_FD, POW2>(t0, q0, fN[r], fdN[r], mask, nbin, cb[r]));
+            for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
         }
-        __syncthreads();  // every warp is done with `buf`
-        if (tid == 0 && it + 2 < ntiles) issue(it + 2);
+        for (; e < cnt; e++) {  // ragged end of the last stage
+            const double t0 = *reinterpret_cast<const double *>(tp + (size_t)e * 8);
+            const double tt0 = HAS_FD ? __dmul_rn(t0, t0) : 0.0;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                red_shared_inc(bin_addr<HAS_FD, POW2>(t0, tt0, fN[r], fdH[r], mask, nbin, cb[r]));
+        }
+        // stage hand-back without a block barrier: the last warp to finish `buf` refills it
+        __syncwarp();
+        if (lane == 0) {
+            const int prev = atomicAdd(&done[buf], 1);
+            if (prev == nwarps - 1) {
+                done[buf] = 0;
+                if (it + 2 < ntiles) {
+                    fence_proxy_async();
+                    issue(it + 2);
+                }
+            }
+        }
     }
+    __syncthreads();  // all histograms complete; tile region idle
 
     if (a.scratch != nullptr) {
         // partial counts -> global scratch [trial/32][bin][32], coalesced across the warp
@@ -279,15 +299,6 @@ __global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restri
     stats[g] = profile_stat([&](int j) { return src[(size_t)j * 32]; }, nbin, nharm, tabs, tabs + nbin);
     if (profiles)
         for (int j = 0; j < nbin; j++) profiles[(size_t)g * nbin + j] = src[(size_t)j * 32];
-}
-
-// (t) -> interleaved (t, q = (0.5*t)*t); rounding identical to the reference's 0.5*t*t
-__global__ void prep_tq_kernel(const double *__restrict__ t, long long n, double2 *__restrict__ tq) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        double v = t[i];
-        tq[i] = make_double2(v, __dmul_rn(__dmul_rn(0.5, v), v));
-    }
 }
 
 // min/max of an fp64 array (range checks for the fast path); out = {min, max}
@@ -339,32 +350,49 @@ struct AsyncBuf {
 // ---- host side --------------------------------------------------------------------------------
 
 struct FoldPlan {
-    int R, W, ctas_per_sm;
+    int R, W, ctas_per_sm, tile_ev;
     uint32_t hist_off, tile_off, smem_bytes;
 };
 
-static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, bool pow2, bool has_fd, FoldPlan *p) {
+static uint32_t tile_region_bytes(int tile_ev, int nbin) {
+    return std::max<uint32_t>(2u * (uint32_t)(tile_ev + TILE_PAD) * 8u, (uint32_t)nbin * 16u);
+}
+
+static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, bool pow2, int regs, FoldPlan *p) {
     const uint32_t blk = (uint32_t)nbin * 128u;
     const uint32_t hist_bytes = (uint32_t)W * R * blk;
-    const uint32_t tile_region =
-        std::max<uint32_t>(2u * (TILE_EV + TILE_PAD) * (has_fd ? 16 : 8), (uint32_t)nbin * 16u);
     uint32_t hist_off, tile_off;
+    int tile_ev = TILE_EV_MAX;
     if (pow2) {
-        uint32_t abs0 = di.dyn_smem_base + 16;
+        uint32_t abs0 = di.dyn_smem_base + SMEM_HDR;
         uint32_t hist_abs = (abs0 + blk - 1) / blk * blk;
         hist_off = hist_abs - di.dyn_smem_base;
-        tile_off = (hist_off - 16 >= tile_region) ? 16u : hist_off + hist_bytes;
+        const uint32_t gap = hist_off - SMEM_HDR;
+        // largest stage that fits in the alignment gap in front of the histograms, if any does
+        int fit = 0;
+        for (int t = TILE_EV_MAX; t >= 256; t -= 64)
+            if (tile_region_bytes(t, nbin) <= gap) {
+                fit = t;
+                break;
+            }
+        if (fit) {
+            tile_ev = fit;
+            tile_off = SMEM_HDR;
+        } else {
+            tile_off = hist_off + hist_bytes;
+        }
     } else {
-        hist_off = 16;
+        hist_off = SMEM_HDR;
         tile_off = hist_off + hist_bytes;
     }
-    uint32_t total = std::max(hist_off + hist_bytes, tile_off + tile_region);
+    uint32_t total = std::max(hist_off + hist_bytes, tile_off + tile_region_bytes(tile_ev, nbin));
     if (total > (uint32_t)di.smem_optin) return false;
     int k_smem = di.smem_per_sm / (int)(total + di.reserved_smem);
-    int k_thr = 1024 / (32 * W);  // fold_kernel is compiled for <= 64 registers/thread
+    const int regs_alloc = (regs + 7) / 8 * 8;                 // register allocation granularity
+    int k_thr = std::min(2048, 65536 / regs_alloc) / (32 * W);  // resident threads allowed by the register file
     int k = std::min(std::min(k_smem, k_thr), 32);
     if (k < 1) return false;
-    p->R = R, p->W = W, p->ctas_per_sm = k;
+    p->R = R, p->W = W, p->ctas_per_sm = k, p->tile_ev = tile_ev;
     p->hist_off = hist_off, p->tile_off = tile_off, p->smem_bytes = total;
     return true;
 }
@@ -379,7 +407,8 @@ static fold_fn_t pick_fold(int R, bool has_fd, bool pow2) {
     switch (R) {
         case 1: return pick_fold_R<1>(has_fd, pow2);
         case 2: return pick_fold_R<2>(has_fd, pow2);
-        default: return pick_fold_R<4>(has_fd, pow2);
+        case 4: return pick_fold_R<4>(has_fd, pow2);
+        default: return pick_fold_R<8>(has_fd, pow2);
     }
 }
 
@@ -475,21 +504,36 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
                 !(flags & HX_FOLD_FORCE_GENERIC);
 
     // ---- plan -------------------------------------------------------------------------------
-    int R = g_fold_R_override ? g_fold_R_override : (nbin <= 32 ? 4 : 2);
+    // (trials per thread, warps per CTA) measured best on B200 for each (nbin, fdot) class
+    // (tools/sweep_table.py); anything that does not fit falls back to "most resident warps".
+    int R, W_pref;
+    if (nbin <= 16) R = 4, W_pref = has_fd ? 4 : 8;
+    else if (nbin <= 32) R = 4, W_pref = has_fd ? 4 : 12;
+    else if (nbin <= 64) R = 2, W_pref = 4;
+    else if (nbin <= 128) R = has_fd ? 1 : 2, W_pref = has_fd ? 12 : 6;
+    else R = 1, W_pref = 6;
+    if (g_fold_R_override) R = g_fold_R_override;
+    if (g_fold_W_override) W_pref = g_fold_W_override;
+    auto kernel_regs = [&](int r, int *out) -> int {
+        cudaFuncAttributes fa;
+        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, pow2))));
+        *out = fa.numRegs;
+        return HX_OK;
+    };
+    int regs = 64;
+    if ((rc = kernel_regs(R, &regs)) != HX_OK) return rc;
     FoldPlan best{};
     int best_res = -1;
-    for (int W = 1; W <= 16; W++) {
-        FoldPlan p;
-        if (!plan_layout(di, nbin, R, W, pow2, has_fd, &p)) continue;
-        if (g_fold_W_override && W != g_fold_W_override) continue;
-        int res = p.ctas_per_sm * W;
-        if (res > best_res) best = p, best_res = res;  // ties: keep the smaller CTA (finer tail)
-    }
-    if (best_res < 0 && R > 1) {  // very large nbin: fall back to one trial per thread
-        R = 1;
+    if (plan_layout(di, nbin, R, W_pref, pow2, regs, &best)) best_res = best.ctas_per_sm * W_pref;
+    for (int pass = 0; pass < 2 && best_res < 0; pass++) {
+        if (pass == 1) {  // very large nbin: one trial per thread
+            if (R == 1) break;
+            R = 1;
+            if ((rc = kernel_regs(R, &regs)) != HX_OK) return rc;
+        }
         for (int W = 1; W <= 16; W++) {
             FoldPlan p;
-            if (!plan_layout(di, nbin, R, W, pow2, has_fd, &p)) continue;
+            if (!plan_layout(di, nbin, R, W, pow2, regs, &p)) continue;
             int res = p.ctas_per_sm * W;
             if (res > best_res) best = p, best_res = res;
         }
@@ -506,36 +550,43 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         if (want < W) {
             int Wn = (int)std::max<long long>(1, want);
             FoldPlan p;
-            if (plan_layout(di, nbin, R, Wn, pow2, has_fd, &p)) best = p, W = Wn;
+            if (plan_layout(di, nbin, R, Wn, pow2, regs, &p)) best = p, W = Wn;
         }
     }
     const long long n_cta_x = (n_tb + W - 1) / W;
     const long long slots = (long long)di.sm_count * best.ctas_per_sm;
+    // Event splitting: every CTA runs for the whole event list, so with few CTA-waves the last,
+    // partially filled wave costs as much as a full one.  Splitting the events s ways multiplies the
+    // number of (shorter) CTAs; pick the s that fills the waves best, charging the extra flush of
+    // the partial histograms (nbin*32 global atomics per warp-slot per split).
     long long ev_splits = 1;
-    if (n_cta_x < slots && n_ev > 0) {
-        ev_splits = std::max<long long>(1, slots / n_cta_x);
-        ev_splits = std::min<long long>(ev_splits, std::max<long long>(1, n_ev / (4 * TILE_EV)));
-        ev_splits = std::min<long long>(ev_splits, 65535);
+    if (n_ev > 0 && (double)n_cta_x / (double)slots < 8.0) {
+        const long long s_max = std::min<long long>(std::max<long long>(1, n_ev / std::max(4 * best.tile_ev, 8192)), 4096);
+        const size_t scratch_bytes = (size_t)n_tb * R * nbin * 32 * sizeof(uint32_t);
+        double best_score = -1.0;
+        for (long long sp = 1; sp <= s_max; sp++) {
+            if (sp > 1 && scratch_bytes > ((size_t)2 << 30)) break;
+            const double waves = (double)(n_cta_x * sp) / (double)slots;
+            const double eff = waves / std::ceil(waves);
+            const double penalty = 1.0 + (sp > 1 ? 4.0 * nbin * (double)sp / (double)n_ev : 0.0);
+            const double score = eff / penalty;
+            if (score > best_score * 1.01) best_score = score, ev_splits = sp;
+            if (waves >= 16.0) break;
+        }
     }
     long long ev_per_split = (n_ev + ev_splits - 1) / std::max<long long>(ev_splits, 1);
-    ev_per_split = (ev_per_split + TILE_EV - 1) / TILE_EV * TILE_EV;
-    if (ev_per_split == 0) ev_per_split = TILE_EV;
+    ev_per_split = (ev_per_split + best.tile_ev - 1) / best.tile_ev * best.tile_ev;
+    if (ev_per_split == 0) ev_per_split = best.tile_ev;
     ev_splits = std::max<long long>(1, (n_ev + ev_per_split - 1) / ev_per_split);
     const bool fused = ev_splits == 1 && d_profiles == nullptr && !(flags & HX_FOLD_FORCE_SCRATCH);
 
     // ---- device temporaries -----------------------------------------------------------------
-    AsyncBuf b_tq(st), b_tab(st), b_scratch(st);
+    AsyncBuf b_tab(st), b_scratch(st);
     std::vector<double> tab;
     host_tables(nbin, tab);
     HX_CUDA_TRY(b_tab.alloc(tab.size() * sizeof(double)));
     HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     const double *ev = d_times;
-    if (has_fd && n_ev > 0) {
-        HX_CUDA_TRY(b_tq.alloc((size_t)n_ev * 16));
-        prep_tq_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>(d_times, n_ev, b_tq.as<double2>());
-        HX_CHECK_LAUNCH("prep_tq_kernel");
-        ev = b_tq.as<double>();
-    }
     if (!fused) {
         size_t sbytes = (size_t)n_tb * R * nbin * 32 * sizeof(uint32_t);
         HX_CUDA_TRY(b_scratch.alloc(sbytes));
@@ -547,6 +598,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     a.ev = ev, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots, a.n_trials = n_trials;
     a.nbin = nbin, a.nharm = nharm;
     a.binmask = pow2 ? (uint32_t)(nbin - 1) << 7 : 0u;
+    a.tile_ev = best.tile_ev;
     a.scale = pow2 ? (double)nbin * 128.0 : 1.0;
     a.stats = d_stats, a.scratch = reinterpret_cast<uint32_t *>(d_scratch), a.tab = reinterpret_cast<double *>(d_tab);
     a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
@@ -603,7 +655,7 @@ int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *s
 }
 
 int hx_fold_set_tuning(int R, int W) {
-    hx::g_fold_R_override = (R == 1 || R == 2 || R == 4) ? R : 0;
+    hx::g_fold_R_override = (R == 1 || R == 2 || R == 4 || R == 8) ? R : 0;
     hx::g_fold_W_override = (W >= 1 && W <= 16) ? W : 0;
     return HX_OK;
 }
