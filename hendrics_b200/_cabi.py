@@ -44,6 +44,7 @@ SIGNATURES = {
     "hx_fold_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
     "hx_fold_set_tuning": (_int, [_int, _int]),
     "hx_qffa_set_tuning": (_int, [_int]),
+    "hx_fold_set_packing": (_int, [_int]),
 }
 
 

@@ -22,6 +22,12 @@
 //     (measured on B200: 26 conflict-free lanes/clk/SM vs 15.8 for LDS+IADD+STS, one issue slot
 //     instead of three and no load->add->store dependency chain); the next group of events is
 //     prefetched into registers before the current group's increments are issued.
+//   * nbin >= 128 (power of two): PACKED counters.  Bins j and j + nbin/2 share one 32-bit word: the
+//     low 6+log2(nbin) bits count every event of the pair, the high bits count those of the upper
+//     bin, so the increment is (low_word & top_bin_bit) | 1 -- one LOP3, no shift -- and the word
+//     offset is the usual AND.  This halves the histogram footprint (twice the resident warps for the
+//     default nbin = 128); words are drained into the global scratch every 2^(6+log2 nbin) - 1 events
+//     at most, before the low field can carry into the high one.
 //   * the statistic epilogue (chi^2 or binned Z^2_n) is fused when a CTA sees all events of its
 //     trials; otherwise counts are reduced into a [trial/32][bin][32] global scratch with coalesced
 //     RED.ADD and a second small kernel computes the statistics.
@@ -47,7 +53,11 @@ struct FoldArgs {
     long long n_trials;
     int nbin;
     int nharm;
-    uint32_t binmask;  // POW2: (nbin-1) << 7
+    uint32_t binmask;  // POW2: (nbin-1) << 7 ; PACKED: (nbin/2-1) << 7
+    uint32_t topbit;   // PACKED: 1 << (6 + log2 nbin), the bit of the scaled phase that selects the upper bin
+    int pack_shift;    // PACKED: 6 + log2 nbin
+    int flush_tiles;   // PACKED: drain the packed words every this many stages
+    long long tb0;     // first 32*R-trial block of this launch (trial batching)
     int tile_ev;       // events per pipeline stage
     double scale;      // POW2: nbin*128, generic: 1
     double *stats;
@@ -59,16 +69,21 @@ struct FoldArgs {
     int *errflag;
 };
 
+enum { MODE_GENERIC = 0, MODE_POW2 = 1, MODE_PACKED = 2 };
+
 // tt = fl(t*t); fdH = 0.5*fd*scale (exact scalings), so fl(tt*fdH) == scale * fl(((0.5*t)*t)*fd)
-template <bool HAS_FD, bool POW2>
-__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double fN, double fdH, uint32_t mask, int nbin,
-                                             uint32_t cb) {
+// Returns the shared-memory word address of the bin; `inc` is the value to add (1 unless PACKED).
+template <bool HAS_FD, int MODE>
+__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double fN, double fdH, uint32_t mask,
+                                             uint32_t topbit, int nbin, uint32_t cb, uint32_t &inc) {
     double x = __dmul_rn(t, fN);
     if (HAS_FD) x = __dadd_rn(x, __dmul_rn(tt, fdH));
-    if (POW2) {
+    inc = 1u;
+    if (MODE != MODE_GENERIC) {
         // x = nbin*128*phase exactly; floor -> low word; bits [7, 7+log2 nbin) are the bin
         double y = __dadd_rd(x, HX_MAGIC);
         uint32_t lo = (uint32_t)__double2loint(y);
+        if (MODE == MODE_PACKED) inc = (lo & topbit) | 1u;
         return (lo & mask) | cb;
     } else {
         double fl = __dsub_rn(__dadd_rd(x, HX_MAGIC), HX_MAGIC);  // floor(x), exact
@@ -78,6 +93,10 @@ __device__ __forceinline__ uint32_t bin_addr(double t, double tt, double fN, dou
         b = min(b, nbin - 1);                            // A4 clamp
         return cb + ((uint32_t)b << 7);
     }
+}
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
 // chi^2 / Z^2_n of one profile; `cnt(j)` returns the count of bin j
@@ -137,13 +156,15 @@ struct GroupSize {
     static constexpr int value = HAS_FD ? (R >= 8 ? 2 : R >= 4 ? 4 : 8) : (R >= 4 ? 2 : 4);
 };
 
-template <int R, bool HAS_FD, bool POW2>
+template <int R, bool HAS_FD, int MODE>
 __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
+    constexpr bool POW2 = MODE != MODE_GENERIC;
+    constexpr bool PACKED = MODE == MODE_PACKED;
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int UE = GroupSize<R, HAS_FD>::value;
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t blk = (uint32_t)a.nbin << 7;  // bytes of one (warp, r) histogram block
+    const uint32_t blk = (uint32_t)a.nbin << (PACKED ? 6 : 7);  // bytes of one (warp, r) histogram block
     const uint32_t hist = sbase + a.hist_off;
     const uint32_t tileb = sbase + a.tile_off;
     const int TILE_EV = a.tile_ev;
@@ -162,7 +183,8 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     }
 
     // trial constants
-    const long long tb = (long long)blockIdx.x * a.warps + warp;  // block of 32*R trials
+    const long long tbl = (long long)blockIdx.x * a.warps + warp;  // block of 32*R trials within this launch
+    const long long tb = a.tb0 + tbl;
     double fN[R], fdH[R];
     uint32_t cb[R];
     bool valid[R];
@@ -212,9 +234,29 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     }
     __syncthreads();
 
-    const uint32_t mask = a.binmask;
+    const uint32_t mask = a.binmask, topbit = a.topbit;
     const int nbin = a.nbin;
     const int nwarps = a.warps;
+
+    // PACKED: drain this thread's packed words into the global scratch and clear them
+    auto drain_packed = [&]() {
+        const int half = nbin >> 1;
+        const uint32_t lowmask = topbit - 1u;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint32_t *dst = a.scratch + ((size_t)(tbl * R + r) * nbin) * 32 + lane;
+            for (int w = 0; w < half; w++) {
+                const uint32_t ad = cb[r] + ((uint32_t)w << 7);
+                const uint32_t v = lds_u32(ad);
+                if (v) {
+                    sts_u32(ad, 0u);
+                    const uint32_t up = v >> a.pack_shift, lowc = (v & lowmask) - up;
+                    if (lowc) atomicAdd(dst + (size_t)w * 32, lowc);
+                    if (up) atomicAdd(dst + (size_t)(w + half) * 32, up);
+                }
+            }
+        }
+    };
 
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
@@ -231,8 +273,12 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
             for (int u = 0; u < UE; u++) {
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    red_shared_inc(bin_addr<HAS_FD, POW2>(cur.t[u], cur.tt[u], fN[r], fdH[r], mask, nbin, cb[r]));
+                for (int r = 0; r < R; r++) {
+                    uint32_t inc;
+                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                    if (PACKED) red_shared_add(ad, inc);
+                    else red_shared_inc(ad);
+                }
             }
 #pragma unroll
             for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
@@ -241,9 +287,14 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
             const double t0 = *reinterpret_cast<const double *>(tp + (size_t)e * 8);
             const double tt0 = HAS_FD ? __dmul_rn(t0, t0) : 0.0;
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                red_shared_inc(bin_addr<HAS_FD, POW2>(t0, tt0, fN[r], fdH[r], mask, nbin, cb[r]));
+            for (int r = 0; r < R; r++) {
+                uint32_t inc;
+                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                if (PACKED) red_shared_add(ad, inc);
+                else red_shared_inc(ad);
+            }
         }
+        if (PACKED && ((it + 1) % a.flush_tiles == 0)) drain_packed();
         // stage hand-back without a block barrier: the last warp to finish `buf` refills it
         __syncwarp();
         if (lane == 0) {
@@ -257,13 +308,17 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
             }
         }
     }
+    if (PACKED) {  // the packed path always finishes through the scratch + fold_stat_kernel
+        drain_packed();
+        return;
+    }
     __syncthreads();  // all histograms complete; tile region idle
 
     if (a.scratch != nullptr) {
         // partial counts -> global scratch [trial/32][bin][32], coalesced across the warp
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            uint32_t *dst = a.scratch + ((size_t)(tb * R + r) * nbin) * 32 + lane;
+            uint32_t *dst = a.scratch + ((size_t)(tbl * R + r) * nbin) * 32 + lane;
             for (int j = 0; j < nbin; j++) {
                 uint32_t c = lds_u32(cb[r] + ((uint32_t)j << 7));
                 if (c) atomicAdd(dst + (size_t)j * 32, c);
@@ -287,15 +342,18 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 }
 
 // scratch [trial/32][bin][32] -> stats (+ optional [trial][nbin] profiles)
-__global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restrict__ scratch, long long n_trials,
-                                                        int nbin, int nharm, const double *__restrict__ tab,
-                                                        double *__restrict__ stats, uint32_t *__restrict__ profiles) {
+// (trials g0 .. g0+n of the grid live at scratch trial index 0 .. n)
+__global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restrict__ scratch, long long g0,
+                                                        long long n, int nbin, int nharm,
+                                                        const double *__restrict__ tab, double *__restrict__ stats,
+                                                        uint32_t *__restrict__ profiles) {
     extern __shared__ double tabs[];
     for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) tabs[i] = tab[i];
     __syncthreads();
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_trials) return;
-    const uint32_t *src = scratch + (size_t)(g >> 5) * nbin * 32 + (g & 31);
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const long long g = g0 + l;
+    const uint32_t *src = scratch + (size_t)(l >> 5) * nbin * 32 + (l & 31);
     stats[g] = profile_stat([&](int j) { return src[(size_t)j * 32]; }, nbin, nharm, tabs, tabs + nbin);
     if (profiles)
         for (int j = 0; j < nbin; j++) profiles[(size_t)g * nbin + j] = src[(size_t)j * 32];
@@ -358,8 +416,9 @@ static uint32_t tile_region_bytes(int tile_ev, int nbin) {
     return std::max<uint32_t>(2u * (uint32_t)(tile_ev + TILE_PAD) * 8u, (uint32_t)nbin * 16u);
 }
 
-static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, bool pow2, int regs, FoldPlan *p) {
-    const uint32_t blk = (uint32_t)nbin * 128u;
+static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, int regs, FoldPlan *p) {
+    const bool pow2 = mode != MODE_GENERIC;
+    const uint32_t blk = (uint32_t)nbin * (mode == MODE_PACKED ? 64u : 128u);
     const uint32_t hist_bytes = (uint32_t)W * R * blk;
     uint32_t hist_off, tile_off;
     int tile_ev = TILE_EV_MAX;
@@ -399,16 +458,21 @@ static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, bool pow2,
 
 typedef void (*fold_fn_t)(const FoldArgs);
 template <int R>
-static fold_fn_t pick_fold_R(bool has_fd, bool pow2) {
-    if (has_fd) return pow2 ? fold_kernel<R, true, true> : fold_kernel<R, true, false>;
-    return pow2 ? fold_kernel<R, false, true> : fold_kernel<R, false, false>;
+static fold_fn_t pick_fold_R(bool has_fd, int mode) {
+    if (has_fd)
+        return mode == MODE_PACKED ? fold_kernel<R, true, MODE_PACKED>
+               : mode == MODE_POW2 ? fold_kernel<R, true, MODE_POW2>
+                                   : fold_kernel<R, true, MODE_GENERIC>;
+    return mode == MODE_PACKED ? fold_kernel<R, false, MODE_PACKED>
+           : mode == MODE_POW2 ? fold_kernel<R, false, MODE_POW2>
+                               : fold_kernel<R, false, MODE_GENERIC>;
 }
-static fold_fn_t pick_fold(int R, bool has_fd, bool pow2) {
+static fold_fn_t pick_fold(int R, bool has_fd, int mode) {
     switch (R) {
-        case 1: return pick_fold_R<1>(has_fd, pow2);
-        case 2: return pick_fold_R<2>(has_fd, pow2);
-        case 4: return pick_fold_R<4>(has_fd, pow2);
-        default: return pick_fold_R<8>(has_fd, pow2);
+        case 1: return pick_fold_R<1>(has_fd, mode);
+        case 2: return pick_fold_R<2>(has_fd, mode);
+        case 4: return pick_fold_R<4>(has_fd, mode);
+        default: return pick_fold_R<8>(has_fd, mode);
     }
 }
 
@@ -420,6 +484,7 @@ static long long g_last_grid = 0, g_last_block = 0, g_last_smem = 0;
 
 static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
+static int g_fold_pack_override = -1;  // -1 auto, 0 never, 1 whenever possible
 
 // cos/sin tables: 2*pi*arange(0, 1, 1/nbin) as hendrics/ffa.py:40,51
 static void host_tables(int nbin, std::vector<double> &tab) {
@@ -500,23 +565,31 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     // non-negative phases (a negative phase in (-0.5, 0) is rounded by the reference's
     // `ph - floor(ph)` before binning; the generic path reproduces that rounding).
     bool nonneg = tmin >= 0 && fmin >= 0 && (fdmin >= 0 || fmin + 0.5 * tmax * fdmin * (1 + 1e-12) > 0);
-    bool pow2 = nbin_p2 && nbin <= 256 && nonneg && phmax * nbin * 128.0 < 1125899906842624.0 &&
-                !(flags & HX_FOLD_FORCE_GENERIC);
+    const bool fast_ok = nbin_p2 && nonneg && phmax * nbin * 128.0 < 1125899906842624.0 &&
+                         !(flags & HX_FOLD_FORCE_GENERIC);
+    int mode = MODE_GENERIC;
+    if (fast_ok && nbin <= 256) mode = MODE_POW2;
+    // packed counters (two bins per word) for the large profiles, where the plain layout leaves
+    // too few resident warps
+    const bool can_pack = fast_ok && nbin >= 128 && nbin <= 512;
+    if (can_pack && (g_fold_pack_override == 1 || (g_fold_pack_override < 0 && nbin >= 128))) mode = MODE_PACKED;
+    if (g_fold_pack_override == 0 && mode == MODE_PACKED) mode = nbin <= 256 ? MODE_POW2 : MODE_GENERIC;
 
     // ---- plan -------------------------------------------------------------------------------
-    // (trials per thread, warps per CTA) measured best on B200 for each (nbin, fdot) class
+    // (trials per thread, warps per CTA) measured best on B200 for each (footprint, fdot) class
     // (tools/sweep_table.py); anything that does not fit falls back to "most resident warps".
+    const int foot = mode == MODE_PACKED ? nbin / 2 : nbin;  // histogram words per trial
     int R, W_pref;
-    if (nbin <= 16) R = 4, W_pref = has_fd ? 4 : 8;
-    else if (nbin <= 32) R = 4, W_pref = has_fd ? 4 : 12;
-    else if (nbin <= 64) R = 2, W_pref = 4;
-    else if (nbin <= 128) R = has_fd ? 1 : 2, W_pref = has_fd ? 12 : 6;
-    else R = 1, W_pref = 6;
+    if (foot <= 16) R = 4, W_pref = has_fd ? 4 : 8;
+    else if (foot <= 32) R = 4, W_pref = has_fd ? 4 : 12;
+    else if (foot <= 64) R = 2, W_pref = 4;
+    else if (foot <= 128) R = 1, W_pref = 12;
+    else R = 1, W_pref = 4;
     if (g_fold_R_override) R = g_fold_R_override;
     if (g_fold_W_override) W_pref = g_fold_W_override;
     auto kernel_regs = [&](int r, int *out) -> int {
         cudaFuncAttributes fa;
-        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, pow2))));
+        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, mode))));
         *out = fa.numRegs;
         return HX_OK;
     };
@@ -524,7 +597,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     if ((rc = kernel_regs(R, &regs)) != HX_OK) return rc;
     FoldPlan best{};
     int best_res = -1;
-    if (plan_layout(di, nbin, R, W_pref, pow2, regs, &best)) best_res = best.ctas_per_sm * W_pref;
+    if (plan_layout(di, nbin, R, W_pref, mode, regs, &best)) best_res = best.ctas_per_sm * W_pref;
     for (int pass = 0; pass < 2 && best_res < 0; pass++) {
         if (pass == 1) {  // very large nbin: one trial per thread
             if (R == 1) break;
@@ -533,7 +606,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         }
         for (int W = 1; W <= 16; W++) {
             FoldPlan p;
-            if (!plan_layout(di, nbin, R, W, pow2, regs, &p)) continue;
+            if (!plan_layout(di, nbin, R, W, mode, regs, &p)) continue;
             int res = p.ctas_per_sm * W;
             if (res > best_res) best = p, best_res = res;
         }
@@ -542,7 +615,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         set_error("hx_fold_search: nbin=%d does not fit in shared memory", nbin);
         return HX_ERR_ARG;
     }
-    const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);
+    const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);  // blocks of 32*R trials (one per warp)
     int W = best.W;
     // few trials: shrink CTAs so that every SM gets one, then split the events across CTAs
     {
@@ -550,10 +623,15 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         if (want < W) {
             int Wn = (int)std::max<long long>(1, want);
             FoldPlan p;
-            if (plan_layout(di, nbin, R, Wn, pow2, regs, &p)) best = p, W = Wn;
+            if (plan_layout(di, nbin, R, Wn, mode, regs, &p)) best = p, W = Wn;
         }
     }
-    const long long n_cta_x = (n_tb + W - 1) / W;
+    // trial batching bounds the global scratch of the non-fused path (1 GiB)
+    const size_t scratch_per_tb = (size_t)R * nbin * 32 * sizeof(uint32_t);
+    long long tb_per_batch = std::max<long long>(W, (long long)(((size_t)1 << 30) / scratch_per_tb) / W * W);
+    const bool must_scratch = mode == MODE_PACKED || d_profiles != nullptr || (flags & HX_FOLD_FORCE_SCRATCH);
+    const long long n_tb_first = must_scratch ? std::min(n_tb, tb_per_batch) : n_tb;
+    const long long n_cta_x = (n_tb_first + W - 1) / W;
     const long long slots = (long long)di.sm_count * best.ctas_per_sm;
     // Event splitting: every CTA runs for the whole event list, so with few CTA-waves the last,
     // partially filled wave costs as much as a full one.  Splitting the events s ways multiplies the
@@ -562,13 +640,11 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     long long ev_splits = 1;
     if (n_ev > 0 && (double)n_cta_x / (double)slots < 8.0) {
         const long long s_max = std::min<long long>(std::max<long long>(1, n_ev / std::max(4 * best.tile_ev, 8192)), 4096);
-        const size_t scratch_bytes = (size_t)n_tb * R * nbin * 32 * sizeof(uint32_t);
         double best_score = -1.0;
         for (long long sp = 1; sp <= s_max; sp++) {
-            if (sp > 1 && scratch_bytes > ((size_t)2 << 30)) break;
             const double waves = (double)(n_cta_x * sp) / (double)slots;
             const double eff = waves / std::ceil(waves);
-            const double penalty = 1.0 + (sp > 1 ? 4.0 * nbin * (double)sp / (double)n_ev : 0.0);
+            const double penalty = 1.0 + ((sp > 1 || must_scratch) ? 4.0 * nbin * (double)sp / (double)n_ev : 0.0);
             const double score = eff / penalty;
             if (score > best_score * 1.01) best_score = score, ev_splits = sp;
             if (waves >= 16.0) break;
@@ -578,7 +654,12 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     ev_per_split = (ev_per_split + best.tile_ev - 1) / best.tile_ev * best.tile_ev;
     if (ev_per_split == 0) ev_per_split = best.tile_ev;
     ev_splits = std::max<long long>(1, (n_ev + ev_per_split - 1) / ev_per_split);
-    const bool fused = ev_splits == 1 && d_profiles == nullptr && !(flags & HX_FOLD_FORCE_SCRATCH);
+    const bool fused = ev_splits == 1 && !must_scratch;
+    if (fused) tb_per_batch = n_tb;
+    if (n_tb / std::max<long long>(tb_per_batch, 1) > 1000000) {
+        set_error("hx_fold_search: trial grid too large");
+        return HX_ERR_ARG;
+    }
 
     // ---- device temporaries -----------------------------------------------------------------
     AsyncBuf b_tab(st), b_scratch(st);
@@ -586,44 +667,56 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     host_tables(nbin, tab);
     HX_CUDA_TRY(b_tab.alloc(tab.size() * sizeof(double)));
     HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    const double *ev = d_times;
-    if (!fused) {
-        size_t sbytes = (size_t)n_tb * R * nbin * 32 * sizeof(uint32_t);
-        HX_CUDA_TRY(b_scratch.alloc(sbytes));
-        HX_CUDA_TRY(cudaMemsetAsync(b_scratch.p, 0, sbytes, st));
-    }
+    const size_t sbytes = fused ? 0 : (size_t)std::min(n_tb, tb_per_batch) * scratch_per_tb;
+    if (!fused) HX_CUDA_TRY(b_scratch.alloc(sbytes));
     void *d_tab = b_tab.p, *d_scratch = fused ? nullptr : b_scratch.p;
 
+    int log2nbin = 0;
+    while ((1 << log2nbin) < nbin) log2nbin++;
     FoldArgs a{};
-    a.ev = ev, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots, a.n_trials = n_trials;
+    a.ev = d_times, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots, a.n_trials = n_trials;
     a.nbin = nbin, a.nharm = nharm;
-    a.binmask = pow2 ? (uint32_t)(nbin - 1) << 7 : 0u;
+    a.binmask = mode == MODE_PACKED ? (uint32_t)(nbin / 2 - 1) << 7 : mode == MODE_POW2 ? (uint32_t)(nbin - 1) << 7 : 0u;
+    a.pack_shift = 6 + log2nbin;
+    a.topbit = 1u << a.pack_shift;
     a.tile_ev = best.tile_ev;
-    a.scale = pow2 ? (double)nbin * 128.0 : 1.0;
+    // the low field of a packed word holds 2^pack_shift - 1 events before it carries
+    a.flush_tiles = std::max(1, (int)(((1u << a.pack_shift) - 1u) / (uint32_t)best.tile_ev));
+    a.scale = mode != MODE_GENERIC ? (double)nbin * 128.0 : 1.0;
     a.stats = d_stats, a.scratch = reinterpret_cast<uint32_t *>(d_scratch), a.tab = reinterpret_cast<double *>(d_tab);
     a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
     a.errflag = d_err;
 
-    fold_fn_t fn = pick_fold(R, has_fd, pow2);
+    fold_fn_t fn = pick_fold(R, has_fd, mode);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem_bytes));
-    dim3 grid((unsigned)n_cta_x, (unsigned)ev_splits);
     if (!g_ev_ok[device]) {
         HX_CUDA_TRY(cudaEventCreate(&g_ev0[device]));
         HX_CUDA_TRY(cudaEventCreate(&g_ev1[device]));
         g_ev_ok[device] = true;
     }
-    HX_CUDA_TRY(cudaEventRecord(g_ev0[device], st));
-    fn<<<grid, W * 32, best.smem_bytes, st>>>(a);
-    HX_CHECK_LAUNCH("fold_kernel");
-    HX_CUDA_TRY(cudaEventRecord(g_ev1[device], st));
-    g_last_timed_device = device;
-    g_last_grid = (long long)n_cta_x * ev_splits, g_last_block = W * 32, g_last_smem = best.smem_bytes;
-    if (!fused) {
-        fold_stat_kernel<<<(unsigned)((n_trials + 255) / 256), 256, 2 * nbin * sizeof(double), st>>>(
-            reinterpret_cast<uint32_t *>(d_scratch), n_trials, nbin, nharm, reinterpret_cast<double *>(d_tab), d_stats,
-            d_profiles);
-        HX_CHECK_LAUNCH("fold_stat_kernel");
+    long long total_ctas = 0;
+    for (long long tb0 = 0; tb0 < n_tb; tb0 += tb_per_batch) {
+        const long long n_tb_b = std::min(tb_per_batch, n_tb - tb0);
+        const long long grid_x = (n_tb_b + W - 1) / W;
+        if (!fused) HX_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, (size_t)n_tb_b * scratch_per_tb, st));
+        a.tb0 = tb0;
+        if (tb0 == 0) HX_CUDA_TRY(cudaEventRecord(g_ev0[device], st));
+        dim3 grid((unsigned)grid_x, (unsigned)ev_splits);
+        fn<<<grid, W * 32, best.smem_bytes, st>>>(a);
+        HX_CHECK_LAUNCH("fold_kernel");
+        if (tb0 + tb_per_batch >= n_tb) HX_CUDA_TRY(cudaEventRecord(g_ev1[device], st));
+        total_ctas += grid_x * ev_splits;
+        if (!fused) {
+            const long long g0 = tb0 * 32 * R;
+            const long long ng = std::min<long long>(n_trials - g0, n_tb_b * 32 * R);
+            fold_stat_kernel<<<(unsigned)((ng + 255) / 256), 256, 2 * nbin * sizeof(double), st>>>(
+                reinterpret_cast<uint32_t *>(d_scratch), g0, ng, nbin, nharm, reinterpret_cast<double *>(d_tab),
+                d_stats, d_profiles);
+            HX_CHECK_LAUNCH("fold_stat_kernel");
+        }
     }
+    g_last_timed_device = device;
+    g_last_grid = total_ctas, g_last_block = W * 32, g_last_smem = best.smem_bytes;
     int herr = 0;
     HX_CUDA_TRY(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     HX_CUDA_TRY(cudaStreamSynchronize(st));
@@ -651,6 +744,11 @@ int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *s
     if (grid) *grid = hx::g_last_grid;
     if (block) *block = hx::g_last_block;
     if (smem_bytes) *smem_bytes = hx::g_last_smem;
+    return HX_OK;
+}
+
+int hx_fold_set_packing(int mode) {
+    hx::g_fold_pack_override = (mode == 0 || mode == 1) ? mode : -1;
     return HX_OK;
 }
 

@@ -135,6 +135,7 @@ int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *s
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);
+int hx_fold_set_packing(int mode); /* 0: never pack counters, 1: whenever possible, other: automatic */
 
 #ifdef __cplusplus
 }

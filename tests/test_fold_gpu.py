@@ -165,3 +165,46 @@ def test_microbench_runs():
 
     for kind in range(4):
         assert _cabi.microbench(kind, reps=2) > 1e9
+
+
+@pytest.mark.parametrize("nbin", [128, 256, 512])
+@pytest.mark.parametrize("fdots", [[0.0], [0.0, 3e-6]])
+def test_packed_counters_equal_plain_and_oracle(nbin, fdots):
+    """nbin >= 128 uses packed (two bins per word) counters; they must give the same bits as the
+    plain layout and as the oracle, including across the periodic drains."""
+    from hendrics_b200 import _cabi
+
+    ts = _events(40000, 1000.0, seed=nbin)
+    freqs = 9.85 + 0.1 * np.arange(200) / 200
+    ref_s, ref_p = C.fold_search(ts, freqs, fdots, nbin, 2, want_profiles=True)
+    lib = _cabi.lib()
+    try:
+        lib.hx_fold_set_packing(1)
+        p_s, p_p = _host_call(ts, freqs, fdots, nbin, 2)
+        lib.hx_fold_set_packing(0)
+        u_s, u_p = _host_call(ts, freqs, fdots, nbin, 2)
+    finally:
+        lib.hx_fold_set_packing(-1)
+    assert np.array_equal(p_p.astype(np.int64), ref_p)
+    assert np.array_equal(u_p.astype(np.int64), ref_p)
+    _assert_stats(p_s, ref_s)
+    _assert_stats(u_s, ref_s)
+    a_s, _ = _host_call(ts, freqs, fdots, nbin, 2, want_profiles=False)  # automatic choice
+    _assert_stats(a_s, ref_s)
+
+
+def test_all_events_in_one_bin_no_counter_overflow():
+    """70000 photons in a single phase bin: more than a 16-bit (or packed 13-bit) field holds."""
+    ts = np.arange(70000, dtype=np.float64)
+    freqs = np.array([1.0, 1.0 + 1.0 / 128 / 70000])
+    for nbin in (16, 128, 256):
+        ref_s, ref_p = C.fold_search(ts, freqs, [0.0], nbin, 1, want_profiles=True)
+        got_s, got_p = _host_call(ts, freqs, [0.0], nbin, 1)
+        assert np.array_equal(got_p.astype(np.int64), ref_p)
+        assert got_p[0, 0, 0] == 70000
+        _assert_stats(got_s, ref_s)
+    # upper half bin of a packed pair
+    ts2 = ts + 0.75
+    ref_s, ref_p = C.fold_search(ts2, freqs[:1], [0.0], 128, 1, want_profiles=True)
+    got_s, got_p = _host_call(ts2, freqs[:1], [0.0], 128, 1)
+    assert np.array_equal(got_p.astype(np.int64), ref_p) and got_p[0, 0, 96] == 70000

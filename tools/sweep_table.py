@@ -9,7 +9,10 @@ lib = _cabi.lib()
 rng = np.random.default_rng(0)
 n_ev = 400_000
 ts = torch.from_numpy(np.sort(rng.uniform(0, 1e5, n_ev))).cuda()
-for nbin in (8, 16, 32, 64, 128, 256):
+import sys as _s
+pack = int(_s.argv[1]) if len(_s.argv) > 1 else -1
+lib.hx_fold_set_packing(pack)
+for nbin in ((128, 256, 512) if pack == 1 else (8, 16, 32, 64, 128, 256)):
     for has_fd in (0, 1):
         n_f, n_fd = (262144, 1) if not has_fd else (4096, 64)
         f = torch.from_numpy(7.4 + 5e-6 * np.arange(n_f)).cuda()
