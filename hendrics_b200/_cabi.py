@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libhxsearch.so")
 
 HX_OK = 0
 HX_ERR_ARG, HX_ERR_CUDA, HX_ERR_NOMEM, HX_ERR_RANGE, HX_ERR_INTERNAL = -1, -2, -3, -4, -5
-HX_FOLD_DEFAULT, HX_FOLD_FORCE_GENERIC, HX_FOLD_FORCE_SCRATCH = 0, 1, 2
+HX_FOLD_DEFAULT, HX_FOLD_FORCE_GENERIC, HX_FOLD_FORCE_SCRATCH, HX_FOLD_EXACT_PHASE = 0, 1, 2, 4
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_u32p = ctypes.POINTER(ctypes.c_uint32)

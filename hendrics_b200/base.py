@@ -78,8 +78,32 @@ def find_peaks_in_image(image, n=5, rough=False, **kwargs):
     image = np.asarray(image)
     flat = image.ravel()
     n = min(n, flat.size)
-    order = np.lexsort((np.arange(flat.size), -flat))[:n]
+    order = None
+    if flat.size >= GPU_TOPK_MIN_SIZE and flat.dtype == np.float64:
+        order = _gpu_topk(np.ascontiguousarray(flat), n)
+    if order is None:
+        order = np.lexsort((np.arange(flat.size), -flat))[:n]
     return np.asarray([np.unravel_index(i, image.shape) for i in order])
+
+
+GPU_TOPK_MIN_SIZE = 1 << 20  # below this a host sort is faster than the H2D copy
+
+
+def _gpu_topk(flat, n):
+    """k streaming arg-max passes on the GPU (csrc/hx_topk.cu); None when no device is usable."""
+    import ctypes
+
+    from . import _cabi
+
+    if _cabi.device_count() < 1:
+        return None
+    idx = np.empty(n, dtype=np.int64)
+    val = np.empty(n, dtype=np.float64)
+    n_out = ctypes.c_int64(0)
+    rc = _cabi.lib().hx_topk(_cabi.dptr(flat), flat.size, int(n), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                             _cabi.dptr(val), ctypes.byref(n_out), 0)
+    _cabi.check(rc)
+    return idx[: n_out.value]
 
 
 # ---- stingray.stats subset  [UPSTREAM-RECALLED: source not under /root/reference] -------------

@@ -41,7 +41,7 @@
 namespace hx {
 
 constexpr int TILE_EV_MAX = 1024;  // events per pipeline stage (runtime: 256..1024, multiple of 64)
-constexpr int TILE_PAD = 8;        // events of slack after each stage (register prefetch may read past cnt)
+constexpr int TILE_PAD = 16;       // events of slack after each stage (register prefetch may read past cnt)
 constexpr uint32_t SMEM_HDR = 32;  // two mbarriers + two "warps done" counters
 
 struct FoldArgs {
@@ -69,17 +69,47 @@ struct FoldArgs {
     int *errflag;
 };
 
-enum { MODE_GENERIC = 0, MODE_POW2 = 1, MODE_PACKED = 2 };
+enum { MODE_GENERIC = 0, MODE_POW2 = 1, MODE_PACKED = 2, MODE_EXACT = 3 };
+
+// floor(x) for |x| < 2^51, exact
+__device__ __forceinline__ double floor_magic(double x) { return __dsub_rn(__dadd_rd(x, HX_MAGIC), HX_MAGIC); }
+
+// MODE_EXACT: phase mod 1 accurate to ~1 ulp of 1.0 whatever the magnitude of t*f (the reference's
+// fp64 phase loses log2(t*f) bits).  Error-free products (p + e == a*b exactly, via FMA) are
+// reduced mod 1 term by term before they are added.  NOT the parity path: it intentionally differs
+// from the reference where fp64 rounding moved a photon across a bin edge.
+__device__ __forceinline__ double exact_phase_frac(double t, double tt, double tte, double f, double h, bool has_fd) {
+    const double p = __dmul_rn(t, f);
+    const double e = __fma_rn(t, f, -p);  // t*f == p + e
+    double s = __dsub_rn(p, floor_magic(p));  // exact, in [0, 1)
+    double small = e;
+    if (has_fd) {
+        const double q = __dmul_rn(tt, h);    // h = 0.5*fd ; t*t == tt + tte
+        const double qe = __fma_rn(tt, h, -q);
+        const double q2 = __dmul_rn(tte, h);
+        s = __dadd_rn(s, __dsub_rn(q, floor_magic(q)));
+        small = __dadd_rn(__dadd_rn(e, qe), q2);
+    }
+    s = __dadd_rn(s, small);
+    return __dsub_rn(s, floor_magic(s));  // back into [0, 1]
+}
 
 // tt = fl(t*t); fdH = 0.5*fd*scale (exact scalings), so fl(tt*fdH) == scale * fl(((0.5*t)*t)*fd)
 // Returns the shared-memory word address of the bin; `inc` is the value to add (1 unless PACKED).
 template <bool HAS_FD, int MODE>
-__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double fN, double fdH, uint32_t mask,
+__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, double fN, double fdH, uint32_t mask,
                                              uint32_t topbit, int nbin, uint32_t cb, uint32_t &inc) {
+    if (MODE == MODE_EXACT) {
+        inc = 1u;
+        const double fr = exact_phase_frac(t, tt, tte, fN, fdH, HAS_FD);
+        int b = __double2loint(__dadd_rd(__dmul_rn(fr, (double)nbin), HX_MAGIC));
+        b = min(b, nbin - 1);
+        return cb + ((uint32_t)b << 7);
+    }
     double x = __dmul_rn(t, fN);
     if (HAS_FD) x = __dadd_rn(x, __dmul_rn(tt, fdH));
     inc = 1u;
-    if (MODE != MODE_GENERIC) {
+    if (MODE == MODE_POW2 || MODE == MODE_PACKED) {
         // x = nbin*128*phase exactly; floor -> low word; bits [7, 7+log2 nbin) are the bin
         double y = __dadd_rd(x, HX_MAGIC);
         uint32_t lo = (uint32_t)__double2loint(y);
@@ -133,9 +163,9 @@ __device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const
     return 2.0 / tot * res;
 }
 
-template <bool HAS_FD, int UE>
+template <bool HAS_FD, int UE, bool EXACT>
 struct EvGroup {
-    double t[UE], tt[UE];
+    double t[UE], tt[UE], tte[EXACT ? UE : 1];
     __device__ __forceinline__ void load(const unsigned char *tp, int e) {
 #pragma unroll
         for (int u = 0; u < UE; u += 2) {
@@ -145,7 +175,10 @@ struct EvGroup {
     }
     __device__ __forceinline__ void squares() {
 #pragma unroll
-        for (int u = 0; u < UE; u++) tt[u] = HAS_FD ? __dmul_rn(t[u], t[u]) : 0.0;
+        for (int u = 0; u < UE; u++) {
+            tt[u] = HAS_FD ? __dmul_rn(t[u], t[u]) : 0.0;
+            if (EXACT) tte[u] = HAS_FD ? __fma_rn(t[u], t[u], -tt[u]) : 0.0;
+        }
     }
 };
 
@@ -158,8 +191,9 @@ struct GroupSize {
 
 template <int R, bool HAS_FD, int MODE>
 __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
-    constexpr bool POW2 = MODE != MODE_GENERIC;
+    constexpr bool POW2 = MODE == MODE_POW2 || MODE == MODE_PACKED;
     constexpr bool PACKED = MODE == MODE_PACKED;
+    constexpr bool EXACT = MODE == MODE_EXACT;
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int UE = GroupSize<R, HAS_FD>::value;
     const uint32_t sbase = smem_u32(smem);
@@ -265,7 +299,55 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         const unsigned char *tp = smem + a.tile_off + (uint32_t)buf * TILE_BYTES;
 
         int e = 0;
-        EvGroup<HAS_FD, UE> cur, nxt;
+        EvGroup<HAS_FD, UE, EXACT> cur, nxt;
+        if constexpr (!HAS_FD) {
+        // Skewed software pipeline: the bin addresses of group g+1 are computed (FP64 pipe) while the
+        // increments of group g are issued (LSU), so the two instruction classes interleave finely
+        // instead of alternating in long runs.
+        uint32_t ad_cur[UE * R], inc_cur[PACKED ? UE * R : 1], ad_nxt[UE * R], inc_nxt[PACKED ? UE * R : 1];
+        auto addresses = [&](EvGroup<HAS_FD, UE, EXACT> &g, uint32_t *ad, uint32_t *incs) {
+            g.squares();
+#pragma unroll
+            for (int u = 0; u < UE; u++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    uint32_t inc;
+                    ad[u * R + r] = bin_addr<HAS_FD, MODE>(g.t[u], g.tt[u], EXACT ? g.tte[u] : 0.0, fN[r], fdH[r], mask,
+                                                           topbit, nbin, cb[r], inc);
+                    if (PACKED) incs[u * R + r] = inc;
+                }
+            }
+        };
+        const int ngroups = cnt / UE;
+        if (ngroups > 0) {
+            cur.load(tp, 0);
+            nxt.load(tp, UE);
+            addresses(cur, ad_cur, inc_cur);
+            for (int g = 0; g < ngroups; g++) {
+                // group g+1 (garbage past the last group: computed, never issued)
+#pragma unroll
+                for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
+                nxt.load(tp, (g + 2) * UE);  // may read the pad after the stage; never used past cnt
+                cur.squares();
+#pragma unroll
+                for (int i = 0; i < UE * R; i++) {
+                    const int u = i / R, r = i % R;
+                    uint32_t inc;
+                    ad_nxt[i] = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], EXACT ? cur.tte[u] : 0.0, fN[r], fdH[r], mask,
+                                                       topbit, nbin, cb[r], inc);
+                    if (PACKED) inc_nxt[i] = inc;
+                    if (PACKED) red_shared_add(ad_cur[i], inc_cur[i]);
+                    else red_shared_inc(ad_cur[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < UE * R; i++) {
+                    ad_cur[i] = ad_nxt[i];
+                    if (PACKED) inc_cur[i] = inc_nxt[i];
+                }
+            }
+            e = ngroups * UE;
+        }
+        } else {
         cur.load(tp, 0);
         for (; e + UE <= cnt; e += UE) {
             nxt.load(tp, e + UE);  // may read the pad after the stage; never used past cnt
@@ -275,7 +357,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     uint32_t inc;
-                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], EXACT ? cur.tte[u] : 0.0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                     if (PACKED) red_shared_add(ad, inc);
                     else red_shared_inc(ad);
                 }
@@ -283,13 +365,15 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
             for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
         }
+        }
         for (; e < cnt; e++) {  // ragged end of the last stage
             const double t0 = *reinterpret_cast<const double *>(tp + (size_t)e * 8);
             const double tt0 = HAS_FD ? __dmul_rn(t0, t0) : 0.0;
+            const double tte0 = (EXACT && HAS_FD) ? __fma_rn(t0, t0, -tt0) : 0.0;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 uint32_t inc;
-                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, tte0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                 if (PACKED) red_shared_add(ad, inc);
                 else red_shared_inc(ad);
             }
@@ -417,7 +501,7 @@ static uint32_t tile_region_bytes(int tile_ev, int nbin) {
 }
 
 static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, int regs, FoldPlan *p) {
-    const bool pow2 = mode != MODE_GENERIC;
+    const bool pow2 = mode == MODE_POW2 || mode == MODE_PACKED;
     const uint32_t blk = (uint32_t)nbin * (mode == MODE_PACKED ? 64u : 128u);
     const uint32_t hist_bytes = (uint32_t)W * R * blk;
     uint32_t hist_off, tile_off;
@@ -462,10 +546,12 @@ static fold_fn_t pick_fold_R(bool has_fd, int mode) {
     if (has_fd)
         return mode == MODE_PACKED ? fold_kernel<R, true, MODE_PACKED>
                : mode == MODE_POW2 ? fold_kernel<R, true, MODE_POW2>
-                                   : fold_kernel<R, true, MODE_GENERIC>;
+               : mode == MODE_EXACT ? fold_kernel<R, true, MODE_EXACT>
+                                    : fold_kernel<R, true, MODE_GENERIC>;
     return mode == MODE_PACKED ? fold_kernel<R, false, MODE_PACKED>
            : mode == MODE_POW2 ? fold_kernel<R, false, MODE_POW2>
-                               : fold_kernel<R, false, MODE_GENERIC>;
+           : mode == MODE_EXACT ? fold_kernel<R, false, MODE_EXACT>
+                                : fold_kernel<R, false, MODE_GENERIC>;
 }
 static fold_fn_t pick_fold(int R, bool has_fd, int mode) {
     switch (R) {
@@ -574,6 +660,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     const bool can_pack = fast_ok && nbin >= 128 && nbin <= 512;
     if (can_pack && (g_fold_pack_override == 1 || (g_fold_pack_override < 0 && nbin >= 128))) mode = MODE_PACKED;
     if (g_fold_pack_override == 0 && mode == MODE_PACKED) mode = nbin <= 256 ? MODE_POW2 : MODE_GENERIC;
+    if (flags & HX_FOLD_EXACT_PHASE) mode = MODE_EXACT;
 
     // ---- plan -------------------------------------------------------------------------------
     // (trials per thread, warps per CTA) measured best on B200 for each (footprint, fdot) class
@@ -682,7 +769,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     a.tile_ev = best.tile_ev;
     // the low field of a packed word holds 2^pack_shift - 1 events before it carries
     a.flush_tiles = std::max(1, (int)(((1u << a.pack_shift) - 1u) / (uint32_t)best.tile_ev));
-    a.scale = mode != MODE_GENERIC ? (double)nbin * 128.0 : 1.0;
+    a.scale = (mode == MODE_POW2 || mode == MODE_PACKED) ? (double)nbin * 128.0 : 1.0;
     a.stats = d_stats, a.scratch = reinterpret_cast<uint32_t *>(d_scratch), a.tab = reinterpret_cast<double *>(d_tab);
     a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
     a.errflag = d_err;

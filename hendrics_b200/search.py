@@ -71,9 +71,16 @@ def _folding_search(
     device=None,
     flags=0,
     return_profiles=False,
+    exact_phase=False,
 ):
     """Upstream ``_folding_search`` fast branch with the (fdot, f) double loop
-    replaced by one K1 launch per segment."""
+    replaced by one K1 launch per segment.
+
+    ``exact_phase=True`` (extension, NOT the parity path) evaluates the phase mod 1 from error-free
+    products instead of the reference's fp64 phase: for very long baselines (|t f| >~ 1e10 cycles)
+    the reference itself warns that fp64 is not enough (hendrics/efsearch.py:199-205, 993-1000)."""
+    if exact_phase:
+        flags = int(flags) | _cabi.HX_FOLD_EXACT_PHASE
     torch = _torch()
     dev = _device(device)
     frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
@@ -162,13 +169,15 @@ def z_n_search(
     return _folding_search(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
 
 
-def fold_profiles(times, frequencies, fdots=0, nbin=128, nharm=0, device=None, flags=0):
+def fold_profiles(times, frequencies, fdots=0, nbin=128, nharm=0, device=None, flags=0, exact_phase=False):
     """Profiles AND statistics of one fold over already-selected, already-zeroed times.
 
     Returns ``(stats (n_fd, n_f), profiles (n_fd, n_f, nbin) int64)``; used by the parity tests
     for the bit-exact profile-count check."""
     torch = _torch()
     dev = _device(device)
+    if exact_phase:
+        flags = int(flags) | _cabi.HX_FOLD_EXACT_PHASE
     ts_d = torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(dev)
     f_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(frequencies), dtype=np.float64)).to(dev)
     fd_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(fdots), dtype=np.float64)).to(dev)

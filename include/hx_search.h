@@ -42,6 +42,9 @@ extern "C" {
 #define HX_FOLD_DEFAULT 0u
 #define HX_FOLD_FORCE_GENERIC 1u /* disable the power-of-two-nbin fast path (testing) */
 #define HX_FOLD_FORCE_SCRATCH 2u /* disable the fused epilogue (testing) */
+#define HX_FOLD_EXACT_PHASE 4u   /* NOT the parity path: phase mod 1 from error-free products (accurate to ~1 ulp
+                                    of 1.0 for any |t*f|), for long baselines where the reference's fp64 phase
+                                    loses log2(t*f) bits; validated against exact rational arithmetic */
 
 /* ---- library / device ------------------------------------------------------------------ */
 

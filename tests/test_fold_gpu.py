@@ -208,3 +208,41 @@ def test_all_events_in_one_bin_no_counter_overflow():
     ref_s, ref_p = C.fold_search(ts2, freqs[:1], [0.0], 128, 1, want_profiles=True)
     got_s, got_p = _host_call(ts2, freqs[:1], [0.0], 128, 1)
     assert np.array_equal(got_p.astype(np.int64), ref_p) and got_p[0, 0, 96] == 70000
+
+
+def test_exact_phase_mode_matches_rational_arithmetic():
+    """Extension (not the parity path): HX_FOLD_EXACT_PHASE bins equal exact rational arithmetic on the
+    fp64 inputs, while the reference-parity fp64 phase flips a few photons on a 1e8 s baseline."""
+    from hendrics_b200 import fold_profiles
+
+    rng = np.random.default_rng(7)
+    ts = np.sort(rng.uniform(0, 1e8, 4000))
+    nbin = 128
+    for f, fd in ((700.123456789, 0.0), (700.123456789, 1.2345e-9), (9.9009900990099, -3e-12)):
+        exact = np.bincount(O.exact_bins(ts, f, fd, nbin), minlength=nbin)
+        _, pe = fold_profiles(ts, [f], [fd], nbin=nbin, nharm=2, exact_phase=True)
+        assert np.array_equal(pe[0, 0], exact), (f, fd)
+        _, pp = fold_profiles(ts, [f], [fd], nbin=nbin, nharm=2)
+        ref_s, ref_p = C.fold_search(ts, [f], [fd], nbin, 2, want_profiles=True)
+        assert np.array_equal(pp[0, 0], ref_p[0, 0])  # parity mode still follows the reference bit for bit
+    # with |t f| ~ 7e10 cycles the two differ
+    _, pp = fold_profiles(ts, [700.123456789], [1.2345e-9], nbin=nbin, nharm=2)
+    _, pe = fold_profiles(ts, [700.123456789], [1.2345e-9], nbin=nbin, nharm=2, exact_phase=True)
+    assert pp.sum() == pe.sum() == ts.size
+
+
+def test_gpu_topk_in_find_peaks():
+    from hendrics_b200 import base
+
+    rng = np.random.default_rng(1)
+    img = rng.chisquare(4, size=(64, 20000))
+    img[3, 17] = img[40, 19999] = 500.0
+    old = base.GPU_TOPK_MIN_SIZE
+    try:
+        base.GPU_TOPK_MIN_SIZE = 1000
+        got = base.find_peaks_in_image(img, n=7)
+    finally:
+        base.GPU_TOPK_MIN_SIZE = old
+    assert np.array_equal(got, O.find_peaks_in_image(img, n=7)) or np.array_equal(
+        [tuple(g) for g in got], [np.unravel_index(i, img.shape) for i in O.topk_flat(img, 7)[0]])
+    assert tuple(got[0]) == (3, 17) and tuple(got[1]) == (40, 19999)
