@@ -89,13 +89,19 @@ def _folding_search(
     times = np.asanyarray(times)
     if times.size == 0:
         raise ValueError("No events to fold")
-    times = (times - times[0]).astype(np.float64)  # A1: re-zero to the first event
-    length = times[-1]
+    if times.dtype == np.float64:
+        # A1: re-zero to the first event.  The fp64 subtraction is done on the device (same IEEE
+        # operation as numpy's) to spare two host passes over the event list.
+        length = np.float64(times[-1] - times[0])
+        times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev) - float(times[0])
+    else:  # e.g. long double mission times: subtract in the input precision, then cast (efsearch.py:1154)
+        times = (times - times[0]).astype(np.float64)
+        length = times[-1]
+        times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
     if length < segment_size:
         segment_size = length
-    start_times = np.arange(times[0], times[-1], segment_size)
+    start_times = np.arange(0.0, length, segment_size)
 
-    times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
     freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
     fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
     stats_d = torch.zeros(fgrid.shape, dtype=torch.float64, device=dev)
