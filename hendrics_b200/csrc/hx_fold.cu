@@ -58,6 +58,7 @@ struct FoldArgs {
     int pack_shift;    // PACKED: 6 + log2 nbin
     int flush_tiles;   // PACKED: drain the packed words every this many stages
     long long tb0;     // first 32*R-trial block of this launch (trial batching)
+    long long n_tb_row;  // ROWFD: 32*R-trial blocks per fdot row (rows padded to a multiple of 32*R)
     int tile_ev;       // events per pipeline stage
     double scale;      // POW2: nbin*128, generic: 1
     double *stats;
@@ -96,9 +97,11 @@ __device__ __forceinline__ double exact_phase_frac(double t, double tt, double t
 
 // tt = fl(t*t); fdH = 0.5*fd*scale (exact scalings), so fl(tt*fdH) == scale * fl(((0.5*t)*t)*fd)
 // Returns the shared-memory word address of the bin; `inc` is the value to add (1 unless PACKED).
+// `m2` is the already rounded fdot term fl(tt*fdH) (computed once per event and thread when the R trials
+// of a thread share their fdot, ROWFD, else per trial).
 template <bool HAS_FD, int MODE>
-__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, double fN, double fdH, uint32_t mask,
-                                             uint32_t topbit, int nbin, uint32_t cb, uint32_t &inc) {
+__device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, double m2, double fN, double fdH,
+                                             uint32_t mask, uint32_t topbit, int nbin, uint32_t cb, uint32_t &inc) {
     if (MODE == MODE_EXACT) {
         inc = 1u;
         const double fr = exact_phase_frac(t, tt, tte, fN, fdH, HAS_FD);
@@ -107,7 +110,7 @@ __device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, do
         return cb + ((uint32_t)b << 7);
     }
     double x = __dmul_rn(t, fN);
-    if (HAS_FD) x = __dadd_rn(x, __dmul_rn(tt, fdH));
+    if (HAS_FD) x = __dadd_rn(x, m2);
     inc = 1u;
     if (MODE == MODE_POW2 || MODE == MODE_PACKED) {
         // x = nbin*128*phase exactly; floor -> low word; bits [7, 7+log2 nbin) are the bin
@@ -165,7 +168,7 @@ __device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const
 
 template <bool HAS_FD, int UE, bool EXACT>
 struct EvGroup {
-    double t[UE], tt[UE], tte[EXACT ? UE : 1];
+    double t[UE], tt[HAS_FD ? UE : 1], tte[(EXACT && HAS_FD) ? UE : 1], m2[HAS_FD ? UE : 1];
     __device__ __forceinline__ void load(const unsigned char *tp, int e) {
 #pragma unroll
         for (int u = 0; u < UE; u += 2) {
@@ -173,11 +176,15 @@ struct EvGroup {
             t[u] = v.x, t[u + 1] = v.y;
         }
     }
-    __device__ __forceinline__ void squares() {
+    // fdH_row: the thread's fdot constant when all its trials share it (ROWFD), else unused
+    __device__ __forceinline__ void squares(double fdH_row = 0.0) {
+        if (HAS_FD) {
 #pragma unroll
-        for (int u = 0; u < UE; u++) {
-            tt[u] = HAS_FD ? __dmul_rn(t[u], t[u]) : 0.0;
-            if (EXACT) tte[u] = HAS_FD ? __fma_rn(t[u], t[u], -tt[u]) : 0.0;
+            for (int u = 0; u < UE; u++) {
+                tt[u] = __dmul_rn(t[u], t[u]);
+                if (EXACT) tte[u] = __fma_rn(t[u], t[u], -tt[u]);
+                m2[u] = __dmul_rn(tt[u], fdH_row);
+            }
         }
     }
 };
@@ -189,8 +196,11 @@ struct GroupSize {
     static constexpr int value = HAS_FD ? (R >= 8 ? 2 : R >= 4 ? 4 : 8) : (R >= 4 ? 2 : 4);
 };
 
-template <int R, bool HAS_FD, int MODE>
+// ROWFD: the R trials of a thread lie in the same fdot row (trial blocks are laid out row by row, rows
+// padded to a multiple of 32*R), so the fdot term is one DMUL per event and thread instead of per trial.
+template <int R, bool HAS_FD, int MODE, bool ROWFD>
 __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
+    static_assert(!ROWFD || HAS_FD, "ROWFD only makes sense with fdot");
     constexpr bool POW2 = MODE == MODE_POW2 || MODE == MODE_PACKED;
     constexpr bool PACKED = MODE == MODE_PACKED;
     constexpr bool EXACT = MODE == MODE_EXACT;
@@ -222,15 +232,39 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     double fN[R], fdH[R];
     uint32_t cb[R];
     bool valid[R];
+    // index of trial r of this thread in stats[] / the (fdot, f) grid (recomputed where needed: keeping
+    // R 64-bit values live through the main loop costs occupancy)
+    auto trial_index = [&](int r) -> long long {
+        if (ROWFD) {
+            const long long ifd = tb / a.n_tb_row;
+            return ifd * a.n_f + ((tb - ifd * a.n_tb_row) * R + r) * 32 + lane;
+        }
+        return (tb * R + r) * 32 + lane;
+    };
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        long long g = (tb * R + r) * 32 + lane;
-        valid[r] = g < a.n_trials;
-        long long gi = valid[r] ? g : 0;
-        long long ifd = gi / a.n_f, jf = gi - ifd * a.n_f;
+        long long ifd, jf;
+        if (ROWFD) {
+            ifd = tb / a.n_tb_row;
+            jf = ((tb - ifd * a.n_tb_row) * R + r) * 32 + lane;
+            valid[r] = jf < a.n_f && ifd * a.n_f + jf < a.n_trials;
+        } else {
+            const long long g = (tb * R + r) * 32 + lane;
+            valid[r] = g < a.n_trials;
+            const long long gi = valid[r] ? g : 0;
+            ifd = gi / a.n_f, jf = gi - ifd * a.n_f;
+        }
+        if (!valid[r]) ifd = 0, jf = 0;
         fN[r] = valid[r] ? __dmul_rn(a.freqs[jf], a.scale) : 0.0;
         fdH[r] = (HAS_FD && valid[r]) ? __dmul_rn(__dmul_rn(0.5, a.fdots[ifd]), a.scale) : 0.0;
         cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * 4u;
+    }
+    // ROWFD: one fdot constant per thread (0 when none of its trials is valid: those bins are discarded)
+    double fdH_row = 0.0;
+    if (ROWFD) {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (valid[r]) fdH_row = fdH[r];
     }
 
     // event range of this CTA
@@ -312,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     uint32_t inc;
-                    ad[u * R + r] = bin_addr<HAS_FD, MODE>(g.t[u], g.tt[u], EXACT ? g.tte[u] : 0.0, fN[r], fdH[r], mask,
+                    ad[u * R + r] = bin_addr<HAS_FD, MODE>(g.t[u], 0.0, 0.0, 0.0, fN[r], fdH[r], mask,
                                                            topbit, nbin, cb[r], inc);
                     if (PACKED) incs[u * R + r] = inc;
                 }
@@ -333,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
                 for (int i = 0; i < UE * R; i++) {
                     const int u = i / R, r = i % R;
                     uint32_t inc;
-                    ad_nxt[i] = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], EXACT ? cur.tte[u] : 0.0, fN[r], fdH[r], mask,
+                    ad_nxt[i] = bin_addr<HAS_FD, MODE>(cur.t[u], 0.0, 0.0, 0.0, fN[r], fdH[r], mask,
                                                        topbit, nbin, cb[r], inc);
                     if (PACKED) inc_nxt[i] = inc;
                     if (PACKED) red_shared_add(ad_cur[i], inc_cur[i]);
@@ -351,13 +385,15 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         cur.load(tp, 0);
         for (; e + UE <= cnt; e += UE) {
             nxt.load(tp, e + UE);  // may read the pad after the stage; never used past cnt
-            cur.squares();
+            cur.squares(fdH_row);
 #pragma unroll
             for (int u = 0; u < UE; u++) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     uint32_t inc;
-                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], cur.tt[u], EXACT ? cur.tte[u] : 0.0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                    const int uu = HAS_FD ? u : 0;
+                    const double m2 = ROWFD ? cur.m2[uu] : (HAS_FD ? __dmul_rn(cur.tt[uu], fdH[r]) : 0.0);
+                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], HAS_FD ? cur.tt[uu] : 0.0, (EXACT && HAS_FD) ? cur.tte[uu] : 0.0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                     if (PACKED) red_shared_add(ad, inc);
                     else red_shared_inc(ad);
                 }
@@ -373,7 +409,8 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 uint32_t inc;
-                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, tte0, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                const double m2 = HAS_FD ? __dmul_rn(tt0, ROWFD ? fdH_row : fdH[r]) : 0.0;
+                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, tte0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                 if (PACKED) red_shared_add(ad, inc);
                 else red_shared_inc(ad);
             }
@@ -421,14 +458,16 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         const uint32_t base = cb[r];
         double st = profile_stat([&](int j) { return lds_u32(base + ((uint32_t)j << 7)); }, nbin, a.nharm, tabs,
                                  tabs + nbin);
-        a.stats[(tb * R + r) * 32 + lane] = st;
+        a.stats[trial_index(r)] = st;
     }
 }
 
 // scratch [trial/32][bin][32] -> stats (+ optional [trial][nbin] profiles)
-// (trials g0 .. g0+n of the grid live at scratch trial index 0 .. n)
-__global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restrict__ scratch, long long g0,
-                                                        long long n, int nbin, int nharm,
+// Scratch slot l of this launch holds the trial with kernel-order index l0 + l.  Kernel order is the grid
+// order g itself (n_fp == 0) or row-padded: index = i_fd * n_fp + j_f with j_f < n_f valid (ROWFD).
+__global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restrict__ scratch, long long l0,
+                                                        long long n, long long n_f, long long n_fp,
+                                                        long long n_trials, int nbin, int nharm,
                                                         const double *__restrict__ tab, double *__restrict__ stats,
                                                         uint32_t *__restrict__ profiles) {
     extern __shared__ double tabs[];
@@ -436,7 +475,13 @@ __global__ void __launch_bounds__(256) fold_stat_kernel(const uint32_t *__restri
     __syncthreads();
     long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
-    const long long g = g0 + l;
+    long long g = l0 + l;
+    if (n_fp > 0) {
+        const long long ifd = g / n_fp, jf = g - ifd * n_fp;
+        if (jf >= n_f) return;
+        g = ifd * n_f + jf;
+    }
+    if (g >= n_trials) return;
     const uint32_t *src = scratch + (size_t)(l >> 5) * nbin * 32 + (l & 31);
     stats[g] = profile_stat([&](int j) { return src[(size_t)j * 32]; }, nbin, nharm, tabs, tabs + nbin);
     if (profiles)
@@ -541,24 +586,24 @@ static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, 
 }
 
 typedef void (*fold_fn_t)(const FoldArgs);
-template <int R>
-static fold_fn_t pick_fold_R(bool has_fd, int mode) {
-    if (has_fd)
-        return mode == MODE_PACKED ? fold_kernel<R, true, MODE_PACKED>
-               : mode == MODE_POW2 ? fold_kernel<R, true, MODE_POW2>
-               : mode == MODE_EXACT ? fold_kernel<R, true, MODE_EXACT>
-                                    : fold_kernel<R, true, MODE_GENERIC>;
-    return mode == MODE_PACKED ? fold_kernel<R, false, MODE_PACKED>
-           : mode == MODE_POW2 ? fold_kernel<R, false, MODE_POW2>
-           : mode == MODE_EXACT ? fold_kernel<R, false, MODE_EXACT>
-                                : fold_kernel<R, false, MODE_GENERIC>;
+template <int R, bool HAS_FD, bool ROWFD>
+static fold_fn_t pick_fold_M(int mode) {
+    return mode == MODE_PACKED ? fold_kernel<R, HAS_FD, MODE_PACKED, ROWFD>
+           : mode == MODE_POW2 ? fold_kernel<R, HAS_FD, MODE_POW2, ROWFD>
+           : mode == MODE_EXACT ? fold_kernel<R, HAS_FD, MODE_EXACT, ROWFD>
+                                : fold_kernel<R, HAS_FD, MODE_GENERIC, ROWFD>;
 }
-static fold_fn_t pick_fold(int R, bool has_fd, int mode) {
+template <int R>
+static fold_fn_t pick_fold_R(bool has_fd, int mode, bool rowfd) {
+    if (!has_fd) return pick_fold_M<R, false, false>(mode);
+    return rowfd ? pick_fold_M<R, true, true>(mode) : pick_fold_M<R, true, false>(mode);
+}
+static fold_fn_t pick_fold(int R, bool has_fd, int mode, bool rowfd) {
     switch (R) {
-        case 1: return pick_fold_R<1>(has_fd, mode);
-        case 2: return pick_fold_R<2>(has_fd, mode);
-        case 4: return pick_fold_R<4>(has_fd, mode);
-        default: return pick_fold_R<8>(has_fd, mode);
+        case 1: return pick_fold_R<1>(has_fd, mode, false);  // one trial per thread: nothing to share
+        case 2: return pick_fold_R<2>(has_fd, mode, rowfd);
+        case 4: return pick_fold_R<4>(has_fd, mode, rowfd);
+        default: return pick_fold_R<8>(has_fd, mode, rowfd);
     }
 }
 
@@ -676,7 +721,8 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     if (g_fold_W_override) W_pref = g_fold_W_override;
     auto kernel_regs = [&](int r, int *out) -> int {
         cudaFuncAttributes fa;
-        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, mode))));
+        const bool rf = has_fd && r >= 2 && n_f >= 32LL * r && mode != MODE_EXACT;
+        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, mode, rf))));
         *out = fa.numRegs;
         return HX_OK;
     };
@@ -702,7 +748,11 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         set_error("hx_fold_search: nbin=%d does not fit in shared memory", nbin);
         return HX_ERR_ARG;
     }
-    const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);  // blocks of 32*R trials (one per warp)
+    // ROWFD: threads with R >= 2 trials take them from one fdot row (rows padded to 32*R frequencies)
+    const bool rowfd = has_fd && R >= 2 && n_f >= 32LL * R && mode != MODE_EXACT;
+    const long long n_tb_row = (n_f + 32LL * R - 1) / (32LL * R);
+    const long long n_fp = rowfd ? n_tb_row * 32LL * R : 0;  // padded row length in kernel order
+    const long long n_tb = rowfd ? n_tb_row * n_fd : (n_trials + 32LL * R - 1) / (32LL * R);  // 32*R-trial blocks
     int W = best.W;
     // few trials: shrink CTAs so that every SM gets one, then split the events across CTAs
     {
@@ -774,7 +824,8 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
     a.errflag = d_err;
 
-    fold_fn_t fn = pick_fold(R, has_fd, mode);
+    a.n_tb_row = n_tb_row;
+    fold_fn_t fn = pick_fold(R, has_fd, mode, rowfd);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem_bytes));
     if (!g_ev_ok[device]) {
         HX_CUDA_TRY(cudaEventCreate(&g_ev0[device]));
@@ -794,11 +845,11 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         if (tb0 + tb_per_batch >= n_tb) HX_CUDA_TRY(cudaEventRecord(g_ev1[device], st));
         total_ctas += grid_x * ev_splits;
         if (!fused) {
-            const long long g0 = tb0 * 32 * R;
-            const long long ng = std::min<long long>(n_trials - g0, n_tb_b * 32 * R);
+            const long long l0 = tb0 * 32 * R;
+            const long long ng = n_tb_b * 32 * R;
             fold_stat_kernel<<<(unsigned)((ng + 255) / 256), 256, 2 * nbin * sizeof(double), st>>>(
-                reinterpret_cast<uint32_t *>(d_scratch), g0, ng, nbin, nharm, reinterpret_cast<double *>(d_tab),
-                d_stats, d_profiles);
+                reinterpret_cast<uint32_t *>(d_scratch), l0, ng, n_f, n_fp, n_trials, nbin, nharm,
+                reinterpret_cast<double *>(d_tab), d_stats, d_profiles);
             HX_CHECK_LAUNCH("fold_stat_kernel");
         }
     }

@@ -61,11 +61,41 @@ __global__ void __launch_bounds__(256) mb_smem_kernel(uint32_t *out, uint32_t se
     if (s != 4u * MB_ITERS) atomicAdd(out, 1u);  // counts are conserved: also a correctness check
 }
 
+// kinds 4/5: the instruction mix of the fold kernel's inner loop, without any memory traffic other
+// than the conflict-free shared atomics: NDP separately rounded FP64 ops + 1 LOP3 + 1 ATOMS per unit
+// (kind 4: NDP = 4, the (f, fdot) path; kind 5: NDP = 2, the f-only path).  Gives the attainable
+// event*trial rate of this mix on the machine, i.e. an empirical ceiling for K1.
+template <int NDP>
+__global__ void __launch_bounds__(256) mb_mix_kernel(uint32_t *out, double a, double b) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const uint32_t base = smem_u32(dsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cb = base + (uint32_t)warp * 2048u + lane * 4u;  // 16 bins x 128 B, private column
+    for (int j = 0; j < 16; j++) sts_u32(cb + j * 128, 0u);
+    double x[MB_ILP];
+#pragma unroll
+    for (int i = 0; i < MB_ILP; i++) x[i] = a * (double)(threadIdx.x + 3 * i + 1);
+    for (int it = 0; it < MB_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < MB_ILP; i++) {
+            double p = __dmul_rn(x[i], a);
+            if (NDP == 4) p = __dadd_rn(p, __dmul_rn(x[i], b));
+            const double y = __dadd_rd(p, HX_MAGIC);
+            red_shared_inc(((uint32_t)__double2loint(y) & 0x780u) | cb);
+            x[i] = p;
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int j = 0; j < 16; j++) s += lds_u32(cb + j * 128);
+    if (s != (uint32_t)MB_ITERS * MB_ILP) atomicAdd(out, 1u);
+}
+
 }  // namespace hx
 
 extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) {
     using namespace hx;
-    if (!ops_per_s || kind < 0 || kind > 3 || reps < 1) {
+    if (!ops_per_s || kind < 0 || kind > 5 || reps < 1) {
         set_error("hx_microbench: bad arguments");
         return HX_ERR_ARG;
     }
@@ -81,7 +111,7 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     HX_CUDA_TRY(cudaEventCreate(&e1));
     const int threads = 256;
     const int grid = di.sm_count * 8 * 4;  // 4 waves of 8 CTAs/SM
-    const size_t smem = (kind >= 2) ? (size_t)(threads / 32) * 4 * 2048 : 0;
+    const size_t smem = (kind >= 4) ? (size_t)(threads / 32) * 2048 : (kind >= 2) ? (size_t)(threads / 32) * 4 * 2048 : 0;
     if (kind == 2) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (kind == 3) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     double best_ms = 1e30;
@@ -91,7 +121,9 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
             case 0: mb_fp64_kernel<0><<<grid, threads>>>(out.as<double>() + 1, 1.0000001, 1e-9); break;
             case 1: mb_fp64_kernel<1><<<grid, threads>>>(out.as<double>() + 1, 1.0000001, 1e-9); break;
             case 2: mb_smem_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
-            default: mb_smem_kernel<3><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
+            case 3: mb_smem_kernel<3><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
+            case 4: mb_mix_kernel<4><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            default: mb_mix_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
         }
         HX_CHECK_LAUNCH("microbench kernel");
         HX_CUDA_TRY(cudaEventRecord(e1));
@@ -110,6 +142,7 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     }
     double per_thread = (kind == 0) ? (double)MB_ITERS * MB_ILP
                       : (kind == 1) ? (double)MB_ITERS * MB_ILP * 2
+                      : (kind >= 4) ? (double)MB_ITERS * MB_ILP  // units (event*trial equivalents)
                                     : (double)MB_ITERS * 4;
     *ops_per_s = per_thread * threads * (double)grid / (best_ms * 1e-3);
     return HX_OK;

@@ -127,6 +127,9 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  *   kind 1: DMUL + DADD pairs (no FMA)     -> FP64 instructions/s
  *   kind 2: shared-memory LDS+IADD+STS read-modify-write, conflict-free -> RMW/s
  *   kind 3: shared-memory atomic add, conflict-free                     -> atomics/s
+ *   kind 4: the (f, fdot) inner-loop mix (2 DMUL + 2 DADD + LOP3 + ATOMS), no other memory traffic
+ *           -> units/s: an empirical ceiling for K1 in event*trials/s
+ *   kind 5: the f-only mix (DMUL + DADD + LOP3 + ATOMS) -> units/s
  * Runs on `device`, blocks, returns the best of `reps` timings.
  */
 int hx_microbench(int kind, int reps, double *ops_per_s, int device);
