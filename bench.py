@@ -471,6 +471,8 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (K1 fold_kernel) ----------------------------------
         peak_ops = _cabi.microbench(1, reps=5, device=local_rank)  # DMUL+DADD issue rate, inst/s
+        # attainable rate of the inner loop's instruction mix (no event loads, full occupancy), units/s
+        mix_ceiling = _cabi.microbench(4 if has_fd else 5, reps=3, device=local_rank)
         alg_ops = algorithmic_ops_per_evtr(has_fd) * units_local
         achieved = alg_ops / (kern_avg_ms * 1e-3)
         exec_ops = (4.0 if has_fd else 2.0) * units_local / (kern_avg_ms * 1e-3)
@@ -489,6 +491,8 @@ def main():
             "kernel": "hx::fold_kernel", "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
             "algorithmic_fp64_ops_per_event_trial": algorithmic_ops_per_evtr(has_fd),
             "executed_fp64_frac": exec_ops / peak_ops,
+            "mix_ceiling_units_per_s": mix_ceiling,
+            "frac_of_mix_ceiling": units_local / (kern_avg_ms * 1e-3) / mix_ceiling,
             "peak_source": "measured in this process: hx_microbench kind 1 (DMUL+DADD issue rate, non-FMA op/s); "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "hbm_peak_gbs": hbm_gbs, "hbm_peak_source": "measured" if os.path.exists(peaks_file) else "fallback",

@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(256) qffa_list_kernel(const QffaHistArgs a, in
 __global__ void __launch_bounds__(256) qffa_rowdft_kernel(const uint32_t *__restrict__ prof, int nprof, int nbin,
                                                           int nharm, const double *__restrict__ tab,
                                                           double *__restrict__ coef /*[C][nprof][nharm][2]*/,
-                                                          unsigned long long *__restrict__ tot /*[C]*/) {
+                                                          unsigned long long *__restrict__ tot /*[C]*/,
+                                                          unsigned long long *__restrict__ rowcnt /*[C][nprof] or null*/) {
     extern __shared__ double tsm[];  // cos | sin
     for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) tsm[i] = tab[i];
     __syncthreads();
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(256) qffa_rowdft_kernel(const uint32_t *__rest
     for (int b = lane; b < nbin; b += 32) cnt += p[b];
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0 && cnt) atomicAdd(&tot[c], cnt);
+    if (lane == 0 && rowcnt) rowcnt[(size_t)c * nprof + row] = cnt;
     for (int h = 1; h <= nharm; h++) {
         double cr = 0.0, sr = 0.0;
         for (int b = lane; b < nbin; b += 32) {
@@ -350,6 +352,42 @@ __global__ void __launch_bounds__(256) qffa_step_kernel(const double *__restrict
     if (threadIdx.x == 0) stats[(size_t)c * n_lq + lq] = 2.0 / (double)tot[c] * res;
 }
 
+// Transient search (hendrics/efsearch.py:407-465, _average_and_z_sub_search): for every averaging level
+// l (groups of 2^l consecutive time slices) the Z^2_n of the summed sub-profiles, written to all rows of
+// the group.  Sums of profiles are sums of their harmonic coefficients, so no profile is touched again.
+__global__ void __launch_bounds__(128) qffa_transient_kernel(const double *__restrict__ coef,
+                                                             const unsigned long long *__restrict__ rowcnt,
+                                                             int nprof, int nharm, int n_levels,
+                                                             double *__restrict__ results /*[C][n_levels][nprof]*/) {
+    const int c = blockIdx.z, level = blockIdx.y;
+    const int n_ave = 1 << level;
+    const int groups = nprof / n_ave;  // int(profiles.shape[0] / n_ave_i)
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    double *out = results + ((size_t)c * n_levels + level) * nprof;
+    if (g >= groups) {
+        // rows not covered by any group keep the reference's initial 0
+        if (g == groups)
+            for (int r = groups * n_ave; r < nprof; r++) out[r] = 0.0;
+        return;
+    }
+    unsigned long long cnt = 0;
+    for (int r = g * n_ave; r < (g + 1) * n_ave; r++) cnt += rowcnt[(size_t)c * nprof + r];
+    double z = 0.0;
+    if (cnt != 0) {  // `if np.sum(new_profiles) == 0: continue`
+        double res = 0.0;
+        for (int h = 0; h < nharm; h++) {
+            double cs = 0.0, sn = 0.0;
+            for (int r = g * n_ave; r < (g + 1) * n_ave; r++) {
+                const double *d = coef + (((size_t)c * nprof + r) * nharm + h) * 2;
+                cs += d[0], sn += d[1];
+            }
+            res += cs * cs + sn * sn;
+        }
+        z = 2.0 / (double)cnt * res;
+    }
+    for (int r = g * n_ave; r < (g + 1) * n_ave; r++) out[r] = z;
+}
+
 typedef void (*qhist_fn_t)(const QffaHistArgs);
 template <int C, bool FAST>
 static qhist_fn_t pick_qhist_c(int mode) {
@@ -383,10 +421,12 @@ static int g_qev_used = 0;
 static long long g_qev_batches = 0;
 static double g_q_last_ms = -1.0;
 
+// transient_levels > 0: instead of the (L, Q) shift search, write the sub-interval statistics of the
+// transient search, d_stats[n_centres][transient_levels][nprof]
 int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double t_last, const double *mean_f,
                          const double *mean_fd, const double *mean_fdd, int64_t n_centres, int nbin, int nprof,
                          const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
-                         uint32_t *d_profiles, cudaStream_t st) {
+                         uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0) {
     if (!d_t || !mean_f || !mean_fd || !mean_fdd || !L || !Q || !d_stats) {
         set_error("hx_qffa_search: null pointer argument");
         return HX_ERR_ARG;
@@ -453,8 +493,9 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
     const size_t coef_elems = (size_t)cmax * nprof * nharm * 2;
     void *d_coef = nullptr;
     Free f4{d_coef, st};
-    HX_CUDA_TRY(cudaMallocAsync(&d_coef, coef_elems * sizeof(double) + (size_t)QF_CMAX * 8, st));
+    HX_CUDA_TRY(cudaMallocAsync(&d_coef, coef_elems * sizeof(double) + (size_t)QF_CMAX * 8 + (size_t)cmax * nprof * 8, st));
     unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(d_coef) + coef_elems);
+    unsigned long long *d_rowcnt = d_tot + QF_CMAX;
 
     if (!g_qev_ok) {
         bool ok = true;
@@ -544,12 +585,22 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
         HX_CUDA_TRY(cudaMemsetAsync(d_tot, 0, (size_t)QF_CMAX * 8, st));
         dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)C);
         qffa_rowdft_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
-            prof, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot);
+            prof, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
+            transient_levels > 0 ? d_rowcnt : nullptr);
         HX_CHECK_LAUNCH("qffa_rowdft_kernel");
-        dim3 g2((unsigned)n_lq, (unsigned)C);
-        qffa_step_kernel<<<g2, 256, step_smem, st>>>(reinterpret_cast<double *>(d_coef), d_tot, nprof, nbin, d_L, d_Q,
-                                                      (int)n_lq, d_base, d_tab, nharm, d_stats + (size_t)c0 * n_lq);
-        HX_CHECK_LAUNCH("qffa_step_kernel");
+        if (transient_levels > 0) {
+            dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
+            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, nharm,
+                                                       transient_levels,
+                                                       d_stats + (size_t)c0 * transient_levels * nprof);
+            HX_CHECK_LAUNCH("qffa_transient_kernel");
+        } else {
+            dim3 g2((unsigned)n_lq, (unsigned)C);
+            qffa_step_kernel<<<g2, 256, step_smem, st>>>(reinterpret_cast<double *>(d_coef), d_tot, nprof, nbin, d_L,
+                                                          d_Q, (int)n_lq, d_base, d_tab, nharm,
+                                                          d_stats + (size_t)c0 * n_lq);
+            HX_CHECK_LAUNCH("qffa_step_kernel");
+        }
     }
     unsigned int flags_h[2] = {0, 0};
     HX_CUDA_TRY(cudaMemcpyAsync(flags_h, reinterpret_cast<char *>(d_unsafe) + (size_t)UNSAFE_CAP * 8, 8,
@@ -568,7 +619,7 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
         const int saved = g_qffa_fast;
         g_qffa_fast = 0;
         int rc = qffa_search_dev_impl(d_t, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin, nprof, L,
-                                      Q, n_lq, nharm, d_stats, d_profiles, st);
+                                      Q, n_lq, nharm, d_stats, d_profiles, st, transient_levels);
         g_qffa_fast = saved;
         return rc;
     }
@@ -604,6 +655,20 @@ int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, do
     return hx::qffa_search_dev_impl(d_times_c, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin,
                                     nprof, L, Q, n_lq, nharm, d_stats, d_profiles,
                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last,
+                            const double *mean_f, const double *mean_fd, int64_t n_centres, int nbin, int nprof,
+                            int nharm, int n_levels, double *d_stats, void *stream) {
+    if (n_levels < 1 || n_levels > 30 || n_centres < 0 || !mean_f || !mean_fd) {
+        hx::set_error("hx_transient_search_dev: bad arguments");
+        return HX_ERR_ARG;
+    }
+    std::vector<double> zeros((size_t)std::max<int64_t>(n_centres, 1), 0.0);
+    const double one_lq[1] = {0.0};
+    return hx::qffa_search_dev_impl(d_times_c, n_ev, t_first, t_last, mean_f, mean_fd, zeros.data(), n_centres, nbin,
+                                    nprof, one_lq, one_lq, 1, nharm, d_stats, nullptr,
+                                    reinterpret_cast<cudaStream_t>(stream), n_levels);
 }
 
 int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, const double *mean_fd,

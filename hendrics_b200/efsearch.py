@@ -43,7 +43,7 @@ log = logging.getLogger("hendrics_b200")
 
 __all__ = [
     "folding_search", "search_with_qffa", "search_with_qffa_step", "check_phase_error_after_casting_to_double",
-    "dyn_folding_search", "analyze_qffa_results", "main_efsearch", "main_zsearch", "z_n_search",
+    "dyn_folding_search", "transient_search", "TransientResults", "analyze_qffa_results", "main_efsearch", "main_zsearch", "z_n_search",
     "epoch_folding_search", "qffa_centres",
 ]
 
@@ -334,6 +334,103 @@ def search_with_qffa(
 
 
 # ---------------------------------------------------------------------------------------------
+# transient search (widening: SURVEY.md section 8f, rank 4)
+# ---------------------------------------------------------------------------------------------
+class TransientResults:
+    """Same fields as hendrics/efsearch.py:488-496."""
+
+    oversample: int = None
+    f0: float = None
+    f1: float = None
+    fdot: float = None
+    nave: np.array = None
+    freqs: np.array = None
+    times: np.array = None
+    stats: np.array = None
+
+
+def transient_search(
+    times, f0, f1, fdot=0, nbin=16, nprof=None, n=1, t0=None, t1=None, oversample=4, force_memmap=False
+):
+    """Search for transient pulsations (hendrics/efsearch.py:499-650).
+
+    For every centre frequency the events are folded into ``nprof`` time slices (K2) and the Z^2_n of
+    the sub-profiles averaged over 1, 2, 4, ... slices is computed from per-slice harmonic coefficients
+    (``hx_transient_search_dev``).  Centres are sharded over ranks like in ``search_with_qffa``."""
+    from . import dist
+
+    if nprof is None:
+        nprof = 4 * 2 * nbin
+
+    times = copy.deepcopy(np.asarray(times))
+    if t0 is None:
+        t0 = times.min()
+    if t1 is None:
+        t1 = times.max()
+    meantime = (t1 + t0) / 2
+    times -= meantime
+
+    maxerr = check_phase_error_after_casting_to_double(np.max(times), f1, fdot)
+    log.info(f"Maximum error on the phase expected when casting to double: {maxerr}")
+    if maxerr > 1 / nbin / 10:
+        warnings.warn("Casting to double produces non-negligible phase errors. Please use shorter light curves.")
+
+    times = times.astype(np.double)
+    length = t1 - t0
+    frequency = (f0 + f1) / 2
+    step = 1 / length / oversample
+    niter = int(np.rint((f1 - f0) / step)) + 2
+    allvalues = list(range(-(niter // 2), niter // 2))
+    if allvalues == []:
+        allvalues = [0]
+    cents = np.array([[np.double(frequency + step * i + 0.12 * step), np.double(fdot + 0)] for i in allvalues])
+    dt = (times[-1] - times[0]) / nprof
+    # `nprof = int(2 ** np.log2(nprof))` in the reference does not truncate (SURVEY Appendix B)
+    n_levels = int(np.log2(int(2 ** np.log2(nprof))))
+    nave = 2 ** np.arange(n_levels)
+
+    times_d = _to_device(times)
+
+    def local(rows):
+        import torch
+
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        mf, mfd = np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1])
+        out = torch.empty((rows.shape[0], n_levels, nprof), dtype=torch.float64, device=times_d.device)
+        with torch.cuda.device(times_d.device):
+            rc = _cabi.lib().hx_transient_search_dev(
+                times_d.data_ptr(), times_d.numel(), float(times[0]), float(times[-1]), _cabi.dptr(mf),
+                _cabi.dptr(mfd), rows.shape[0], int(nbin), int(nprof), int(n), int(n_levels), out.data_ptr(),
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _cabi.check(rc)
+        return out.cpu().numpy()
+
+    all_results = dist.sharded_rows(local, cents)  # (centres, levels, nprof)
+    final_shape = (nave.size, all_results.shape[2], all_results.shape[0])
+    if np.prod(final_shape) > 1e7 or force_memmap:
+        import tempfile
+
+        tmp = tempfile.NamedTemporaryFile(delete=True).name + "_hen.npy"
+        stats = np.lib.format.open_memmap(tmp, mode="w+", dtype=np.float64, shape=final_shape)
+    else:
+        stats = np.empty(final_shape)
+    for i in range(nave.size):
+        stats[i] = all_results[:, i, :].T
+
+    results = TransientResults()
+    results.oversample = oversample
+    results.f0 = f0
+    results.f1 = f1
+    results.fdot = fdot
+    results.nave = nave
+    results.freqs = cents[:, 0].copy()
+    results.times = dt * np.arange(all_results.shape[2])
+    results.stats = stats
+    return results
+
+
+# ---------------------------------------------------------------------------------------------
 # candidates
 # ---------------------------------------------------------------------------------------------
 def get_boundaries_from_level(x, y, level, x0):
@@ -469,7 +566,8 @@ def _common_parser(args=None):
     parser.add_argument("--ffa", default=False, action="store_true",
                         help="Use *the* Fast Folding Algorithm by Staelin+69. (not available in hendrics_b200)")
     parser.add_argument("--transient", default=False, action="store_true",
-                        help="Look for transient emission (not available in hendrics_b200)")
+                        help="Look for transient emission (the dynamic Z search arrays are saved as "
+                        "<root>_transient.npz; the reference's animated GIF needs matplotlib)")
     parser.add_argument("--expocorr", default=False, action="store_true",
                         help="Correct for the exposure of the profile bins (not available in hendrics_b200)")
     parser.add_argument("--find-candidates", default=False, action="store_true",
@@ -558,7 +656,7 @@ def _common_main(args, func):
 
     if func != z_n_search and args.fast:
         raise ValueError("The fast option is only available for z searches")
-    for flag, name in [(args.ffa, "--ffa (Fast Folding Algorithm)"), (args.transient, "--transient"),
+    for flag, name in [(args.ffa, "--ffa (Fast Folding Algorithm)"),
                        (args.deorbit_par is not None, "--deorbit-par (PINT)")]:
         if flag:
             raise NotImplementedError(f"{name} is outside the B200 search hot path (SURVEY.md section 8f)")
@@ -606,6 +704,21 @@ def _common_main(args, func):
             oversample = assign_value_if_none(args.oversample, 4 * n)
         else:
             oversample = assign_value_if_none(args.oversample, 2)
+
+        if args.transient:
+            # efsearch.py:1831-1845; the reference renders an animated GIF (matplotlib + imageio, both
+            # unavailable here): the arrays it is drawn from are saved instead
+            tr = transient_search(
+                events.time, args.fmin, args.fmax, fdot=0, nbin=args.nbin, n=n, nprof=args.n_transient_intervals,
+                oversample=oversample, force_memmap=args.force_memmap,
+            )
+            from . import dist as _dist
+
+            if _dist.rank() == 0:
+                np.savez(out_fname + "_transient.npz", nave=tr.nave, freqs=tr.freqs, times=tr.times,
+                         stats=np.asarray(tr.stats), f0=tr.f0, f1=tr.f1, fdot=tr.fdot, oversample=tr.oversample)
+            if not args.fast:
+                continue
 
         if not args.fast:
             fdotmin = args.fdotmin if args.fdotmin is not None else 0

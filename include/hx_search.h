@@ -103,6 +103,16 @@ int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, do
                        const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
                        uint32_t *d_profiles, void *stream);
 
+/* ---- transient search (widening) ----------------------------------------
+ * Replaces hendrics/efsearch.py:468-485 (_transient_search_step) = _fast_phase_fdot + histogram2d +
+ * _average_and_z_sub_search (:407-465) for `n_centres` centre frequencies: for every averaging level
+ * l < n_levels (groups of 2^l consecutive time slices) the Z^2_nharm of each group's summed profile.
+ *   d_stats [n_centres * n_levels * nprof]   (centre, level, time slice)
+ * n_levels = int(log2(nprof)) in the reference.  Same conventions as hx_qffa_search_dev. */
+int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last,
+                            const double *mean_f, const double *mean_fd, int64_t n_centres, int nbin, int nprof,
+                            int nharm, int n_levels, double *d_stats, void *stream);
+
 /* ---- K4: unbinned Z^2_n (extension; oracle formula hendrics/efsearch.py:366-404) ---------
  * stats[i*n_f + j] = 2/N * sum_{k=1..nharm} [(sum cos 2 pi k phi)^2 + (sum sin 2 pi k phi)^2]
  * with phi = frac(t*f + 0.5*t*t*fd) per event.

@@ -15,6 +15,7 @@ What it restates (file:line are relative to the reference tree, ``/root/referenc
     hendrics/efsearch.py:876-925   ``search_with_qffa_step``
     hendrics/efsearch.py:928-1089  ``search_with_qffa``
     hendrics/efsearch.py:1141-1193 ``folding_search``
+    hendrics/efsearch.py:407-650   ``_average_and_z_sub_search`` / ``_transient_search_step`` / ``transient_search``
     hendrics/efsearch.py:199-205   ``check_phase_error_after_casting_to_double``
     hendrics/ffa.py:38-157         cached harmonics, ``_z_n_fast_cached`` (binned Z^2_n)
     hendrics/base.py:667-693       ``_hist2d_numba_seq`` / ``hist2d_numba_seq``
@@ -597,6 +598,78 @@ def search_with_qffa(
     if search_fdot:
         return all_fgrid.T, all_fdotgrid.T, all_stats.T, step, fdotstep, length
     return all_fgrid.T[0], all_stats.T[0], step, length
+
+
+# --------------------------------------------------------------------------------------
+# transient search (hendrics/efsearch.py:407-650)
+# --------------------------------------------------------------------------------------
+def average_and_z_sub_search(profiles, n=2):
+    """hendrics/efsearch.py:407-465 (`int(2 ** np.log2(nprof))` does not truncate, as in the reference)."""
+    profiles = np.asarray(profiles, dtype=np.float64)
+    nprof = len(profiles)
+    nprof = int(2 ** np.log2(nprof))
+    profiles = profiles[:nprof]
+    nbin = len(profiles[0])
+    n_log_ave_max = int(np.log2(nprof))
+    results = np.zeros((n_log_ave_max, nprof))
+    twopiphases = 2 * np.pi * np.arange(0, 1, 1 / nbin)
+    n_ave = 2 ** np.arange(n_log_ave_max)
+    for ave_i in range(len(n_ave)):
+        n_ave_i = n_ave[ave_i]
+        shape_0 = int(profiles.shape[0] / n_ave_i)
+        for i in range(shape_0):
+            new_profiles = np.sum(profiles[i * n_ave_i : (i + 1) * n_ave_i], axis=0)
+            if np.sum(new_profiles) == 0:
+                continue
+            z = z_n_fast(twopiphases, new_profiles, n)
+            results[ave_i, i * n_ave_i : (i + 1) * n_ave_i] = z
+    return n_ave, results
+
+
+def transient_search_step(times, mean_f, mean_fdot=0, nbin=16, nprof=64, n=1):
+    """hendrics/efsearch.py:468-485."""
+    phases = fast_phase_fdot(times, mean_f, mean_fdot)
+    profiles = histogram2d(phases, times, range=[[0, 1], [times[0], times[-1]]], bins=(nbin, nprof)).T
+    return average_and_z_sub_search(profiles, n=n)
+
+
+def transient_centres(f0, f1, length, oversample=4, fdot=0):
+    """Centre list of hendrics/efsearch.py:573-592."""
+    frequency = (f0 + f1) / 2
+    step = 1 / length / oversample
+    niter = int(np.rint((f1 - f0) / step)) + 2
+    allvalues = list(range(-(niter // 2), niter // 2))
+    if allvalues == []:
+        allvalues = [0]
+    return [(np.double(frequency + step * i + 0.12 * step), np.double(fdot + 0)) for i in allvalues]
+
+
+def transient_search(times, f0, f1, fdot=0, nbin=16, nprof=None, n=1, t0=None, t1=None, oversample=4):
+    """hendrics/efsearch.py:499-650; returns (nave, freqs, times, stats[nave, nprof, n_centres])."""
+    if nprof is None:
+        nprof = 4 * 2 * nbin
+    times = copy.deepcopy(np.asarray(times))
+    if t0 is None:
+        t0 = times.min()
+    if t1 is None:
+        t1 = times.max()
+    meantime = (t1 + t0) / 2
+    times = times - meantime
+    times = times.astype(np.double)
+    length = t1 - t0
+    cents = transient_centres(f0, f1, length, oversample, fdot)
+    dt = (times[-1] - times[0]) / nprof
+    all_results, all_freqs = [], []
+    for mean_f, mean_fdot in cents:
+        nave, results = transient_search_step(times, mean_f, mean_fdot=mean_fdot, nbin=nbin, nprof=nprof, n=n)
+        all_results.append(results)
+        all_freqs.append(mean_f)
+    all_results = np.asarray(all_results)  # (centres, levels, nprof)
+    tgrid = dt * np.arange(all_results.shape[2])
+    stats = np.empty((nave.size, all_results.shape[2], all_results.shape[0]))
+    for i in range(nave.size):
+        stats[i] = all_results[:, i, :].T
+    return nave, np.asarray(all_freqs), tgrid, stats
 
 
 # --------------------------------------------------------------------------------------

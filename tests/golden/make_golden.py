@@ -10,6 +10,7 @@ IN-TREE reference code (numpy/numba only) and runs unmodified:
 
     hendrics.efsearch: _fast_phase, _fast_phase_fdot, _fast_phase_fddot, shift_and_sum, _fast_step,
                        search_with_qffa_step, search_with_qffa, z_n_fast, folding_search,
+                       _average_and_z_sub_search, transient_search,
                        check_phase_error_after_casting_to_double
     hendrics.ffa:      _z_n_fast_cached, z_n_fast_cached, z_n_fast_cached_all, h_test
     hendrics.base:     hist2d_numba_seq / histogram2d, find_peaks_in_image(rough=True)
@@ -59,6 +60,9 @@ def main():
     from hendrics import ffa as hffa
 
     from hendrics_b200.fake import simulate_events
+
+    # tqdm is one of the stubbed third-party modules: make the progress-bar wrapper the identity
+    hef.show_progress = lambda x: x
 
     out = {}
 
@@ -153,6 +157,20 @@ def main():
                           fdots=cap["fd"], step=r[2], length=r[3]))
     for i, g in enumerate(grids):
         out[f"grid{i}"] = {k: np.asarray(v) for k, v in g.items()}
+
+    # ---- 7. transient search (in-tree, efsearch.py:407-650) ---------------------------------------
+    prof = rng.poisson(20, size=(16, 32)).astype(np.float64)
+    prof[5] = 0
+    nave, res = hef._average_and_z_sub_search(prof, n=2)
+    out["transient_sub"] = dict(profiles=prof, nave=np.asarray(nave), results=np.asarray(res))
+    ts = simulate_events(15000, 128.0, seed=41) + 8e7
+    np.random.seed(7)
+    tr = hef.transient_search(ts, 9.85, 9.95, nbin=16, n=2, oversample=4)
+    out["transient_full"] = dict(times=ts, nave=np.asarray(tr.nave), freqs=np.asarray(tr.freqs), tgrid=np.asarray(tr.times),
+                                 stats=np.asarray(tr.stats))
+    tr = hef.transient_search(ts, 9.88, 9.92, fdot=1e-6, nbin=32, nprof=96, n=1, oversample=2)
+    out["transient_np96"] = dict(times=ts, nave=np.asarray(tr.nave), freqs=np.asarray(tr.freqs), tgrid=np.asarray(tr.times),
+                                 stats=np.asarray(tr.stats))
 
     for name, d in out.items():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **d)

@@ -77,3 +77,38 @@ def test_cli_errors(evfile):
         main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "-n", "2", "-N", "2", "--fast"])
     with pytest.raises(NotImplementedError):
         main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "--ffa"])
+
+
+def test_transient_cli(evfile):
+    from hendrics_b200.efsearch import main_zsearch
+
+    np.random.seed(2)
+    out = main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "-n", "16", "--transient"])
+    assert out == []  # like the reference: `--transient` alone produces only the transient product
+    npz = evfile.replace("_ev.p", "") + "_Z22_9.85-9.95Hz_transient.npz"
+    assert os.path.exists(npz)
+    d = np.load(npz)
+    assert d["stats"].shape[0] == d["nave"].size and d["stats"].shape[2] == d["freqs"].size
+    k = np.unravel_index(np.argmax(d["stats"][-1]), d["stats"][-1].shape)
+    assert abs(d["freqs"][k[1]] - PULSE_F) < 2 / 25.25
+
+
+def test_dyn_folding_search_and_candidates(evfile):
+    from hendrics_b200 import z_n_search
+    from hendrics_b200.efsearch import _analyze_qffa_results, dyn_folding_search, search_with_qffa
+    from hendrics_b200.io import EFPeriodogram, load_events
+
+    ev = load_events(evfile)
+    times, freqs, stats = dyn_folding_search(ev, 9.85, 9.95, func=z_n_search, oversample=2, time_step=5.0, nharm=2, nbin=16)
+    assert stats.shape == (times.size, freqs.size) and times.size == 5
+    # each window equals a direct search on its events
+    sel = ev.time[(ev.time >= 8e7) & (ev.time < 8e7 + 5.0)]
+    f0, s0 = z_n_search(sel, freqs, nharm=2, nbin=16)
+    np.testing.assert_allclose(stats[0], s0, rtol=1e-12)
+    np.random.seed(3)
+    r = search_with_qffa(ev.time, 9.85, 9.95, nbin=16, n=2, silent=True)
+    ef = EFPeriodogram(r[0], r[2], "Z2n", 16, 2, fdots=r[1], M=1, oversample=8, ncounts=ev.time.size, filename=evfile,
+                       pepoch=56000.0)
+    rows = _analyze_qffa_results(ef)
+    assert 1 <= len(rows) <= 5 and abs(rows[0]["f"] - PULSE_F) < 2 / 25.25
+    assert rows[0]["power"] == r[2].max() and rows[0]["f_idx"] == np.unravel_index(np.argmax(r[2]), r[2].shape)[0]

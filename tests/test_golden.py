@@ -125,3 +125,19 @@ def test_folding_search_grids_vs_reference(i):
                         fdotmin=float(g["fdmin"]), fdotmax=float(g["fdmax"]))
     assert np.array_equal(cap["f"], g["freqs"]) and np.array_equal(cap["fd"], g["fdots"])
     assert r2[2] == float(g["step"]) and r2[3] == float(g["length"])
+
+
+def test_transient_search_oracle_vs_reference():
+    g = load("transient_sub")
+    nave, res = O.average_and_z_sub_search(g["profiles"], n=2)
+    assert np.array_equal(nave, g["nave"])
+    np.testing.assert_allclose(res, g["results"], rtol=1e-12)
+    assert np.all(res[0, 5] == 0)  # empty sub-profile keeps the initial 0
+    for name, kw in (("transient_full", dict(nbin=16, n=2, oversample=4, f0=9.85, f1=9.95)),
+                     ("transient_np96", dict(nbin=32, nprof=96, n=1, oversample=2, f0=9.88, f1=9.92, fdot=1e-6))):
+        g = load(name)
+        kw = dict(kw)
+        f0, f1 = kw.pop("f0"), kw.pop("f1")
+        nave, freqs, tg, stats = O.transient_search(g["times"], f0, f1, **kw)
+        assert np.array_equal(nave, g["nave"]) and np.array_equal(freqs, g["freqs"]) and np.array_equal(tg, g["tgrid"])
+        np.testing.assert_allclose(stats, g["stats"], rtol=1e-11)

@@ -64,3 +64,19 @@ def test_binned_z_of_reference_profiles():
         assert np.isclose(stats[0, 0], g["z2"][i], rtol=RTOL)
         stats4, _ = fold_profiles(np.sort(ts), [1.0], [0.0], nbin=nbin, nharm=4)
         assert np.isclose(stats4[0, 0], g["z4"][i], rtol=RTOL)
+
+
+def test_transient_search_cuda_vs_reference():
+    from hendrics_b200.efsearch import transient_search
+
+    for name, kw in (("transient_full", dict(nbin=16, n=2, oversample=4, f0=9.85, f1=9.95)),
+                     ("transient_np96", dict(nbin=32, nprof=96, n=1, oversample=2, f0=9.88, f1=9.92, fdot=1e-6))):
+        g = load(name)
+        kw = dict(kw)
+        f0, f1 = kw.pop("f0"), kw.pop("f1")
+        np.random.seed(7)
+        tr = transient_search(g["times"], f0, f1, **kw)
+        assert np.array_equal(tr.nave, g["nave"]) and np.array_equal(tr.freqs, g["freqs"])
+        assert np.array_equal(tr.times, g["tgrid"])
+        assert tr.stats.shape == g["stats"].shape
+        np.testing.assert_allclose(tr.stats, g["stats"], rtol=RTOL)
