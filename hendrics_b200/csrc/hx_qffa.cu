@@ -259,6 +259,309 @@ __global__ void __launch_bounds__(256) qffa_list_kernel(const QffaHistArgs a, in
     }
 }
 
+
+// ================================================================================================
+// K2-lane: the `--fast` 2-D profiles with lane = centre frequency (the K1 layout applied to K2).
+//
+// qffa_hist_kernel (lane = event) is bound by bank conflicts of its shared-memory atomics: 32 photons
+// of a warp hit 32 random phase bins.  Here every lane owns one centre frequency (R per thread) and a
+// private [bin][lane] histogram column, every increment is a conflict-free ATOMS, and the events --
+// sorted in time -- are walked one time slice ("row") after the other: the row boundaries are found
+// once per call by binary search (the row index fl(fl(t - t0) * delta1) is monotone in t), the inner
+// loop is K1's straight-line loop, and a column is drained into prof[row] when its row ends.
+// Photons with |t| < t_safe, for which `phase - floor(phase)` is not exact, are folded like the others
+// and then corrected by qffa_fix_kernel, which re-bins them with the reference's operation sequence.
+// Requires power-of-two nbin and sorted times; otherwise the lane = event kernel above is used.
+// ================================================================================================
+struct QLaneArgs {
+    const double *t;
+    long long n_ev;
+    const long long *row_start;  // [nprof + 1] first event of every row; row_start[nprof] = first dropped event
+    const double *f, *fd, *fdd;  // [n_c] centre constants of this batch (device)
+    int n_c;
+    int nbin, nprof;
+    long long ev_per_cta;  // events per CTA along grid.y (even), over [0, row_start[nprof])
+    double scale;      // nbin * 128
+    uint32_t binmask;  // (nbin-1) << 7, packed: (nbin/2-1) << 7
+    uint32_t topbit;
+    int pack_shift;
+    int flush_events;  // packed: drain at least every this many events
+    uint32_t *prof;    // [ceil(n_c/32)][nprof][nbin][32]
+    int warps;
+    uint32_t hist_off, tile_off;
+    int tile_ev;
+    int *errflag;
+};
+
+template <int R, int MODE, bool PACKED>
+__global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int UE = 4;
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t blk = (uint32_t)a.nbin << (PACKED ? 6 : 7);
+    const uint32_t hist = sbase + a.hist_off;
+    const uint32_t tileb = sbase + a.tile_off;
+    const int TILE_EV = a.tile_ev;
+    const uint32_t TILE_BYTES = (uint32_t)(TILE_EV + 16) * 8u;
+    int *done = reinterpret_cast<int *>(smem + 16);
+    const int nbin = a.nbin, nprof = a.nprof, nwarps = a.warps;
+    if ((hist & (blk - 1)) != 0) {
+        if (tid == 0) atomicExch(a.errflag, 1);
+        return;
+    }
+    for (uint32_t o = tid * 4; o < (uint32_t)nwarps * R * blk; o += blockDim.x * 4) sts_u32(hist + o, 0u);
+
+    // centre constants: slot = 32 centres
+    const long long slot0 = ((long long)blockIdx.x * nwarps + warp) * R;
+    double fN[R], fdN[MODE >= 1 ? R : 1], fddN[MODE >= 2 ? R : 1];
+    uint32_t cb[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const long long c = (slot0 + r) * 32 + lane;
+        const bool valid = c < a.n_c;
+        fN[r] = valid ? __dmul_rn(a.f[c], a.scale) : 0.0;
+        if (MODE >= 1) fdN[r] = valid ? __dmul_rn(a.fd[c], a.scale) : 0.0;
+        if (MODE >= 2) fddN[r] = valid ? __dmul_rn(a.fdd[c], a.scale) : 0.0;
+        cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * 4u;
+    }
+
+    // events of this CTA (a contiguous chunk; rows may be shared with the neighbouring CTAs: drains are atomic)
+    const long long n_valid = a.row_start[nprof];
+    const long long ev_lo = min(n_valid, (long long)blockIdx.y * a.ev_per_cta);
+    const long long ev_hi = min(n_valid, ev_lo + a.ev_per_cta);
+    int j0;  // row of the first event: last j with row_start[j] <= ev_lo
+    {
+        int lo = 0, hi = nprof;  // invariant: row_start[lo] <= ev_lo, answer in [lo, hi)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.row_start[mid] <= ev_lo) lo = mid;
+            else hi = mid;
+        }
+        j0 = lo;
+    }
+    const int j1 = nprof;
+    const long long es = ev_lo;  // ev_per_cta is even: 16-byte aligned stream start
+    const int ntiles = ev_hi > es ? (int)((ev_hi - es + TILE_EV - 1) / TILE_EV) : 0;
+    const uint32_t bar[2] = {sbase, sbase + 8};
+    auto issue = [&](int it) {
+        const long long s = es + (long long)it * TILE_EV;
+        const int cnt = (int)min((long long)TILE_EV, ev_hi - s);
+        const uint32_t bytes = (uint32_t)cnt * 8u, bulk = bytes & ~15u;
+        const uint32_t dst = tileb + (uint32_t)(it & 1) * TILE_BYTES;
+        const char *src = reinterpret_cast<const char *>(a.t) + s * 8;
+        if (bytes != bulk)
+            *reinterpret_cast<double *>(smem + a.tile_off + (uint32_t)(it & 1) * TILE_BYTES + bulk) =
+                *reinterpret_cast<const double *>(src + bulk);
+        if (bulk) {
+            mbar_expect_tx(bar[it & 1], bulk);
+            bulk_g2s(dst, src, bulk, bar[it & 1]);
+        } else {
+            mbar_arrive(bar[it & 1]);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(bar[0], 1);
+        mbar_init(bar[1], 1);
+        done[0] = 0, done[1] = 0;
+        fence_mbar_init();
+        fence_proxy_async();
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    __syncthreads();
+
+    const uint32_t mask = a.binmask, topbit = a.topbit;
+    // drain this thread's columns into prof[slot][row][bin][lane] (coalesced across the warp) and clear them
+    const long long n_slots = ((long long)a.n_c + 31) >> 5;
+    auto drain = [&](int row) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (slot0 + r >= n_slots) continue;  // padding slot of the last CTA: nothing to keep
+            uint32_t *dst = a.prof + (((size_t)(slot0 + r) * nprof + row) * nbin) * 32 + lane;
+            if (PACKED) {
+                const int half = nbin >> 1;
+                const uint32_t lowmask = topbit - 1u;
+                for (int w = 0; w < half; w++) {
+                    const uint32_t ad = cb[r] + ((uint32_t)w << 7);
+                    const uint32_t v = lds_u32(ad);
+                    if (v) {
+                        sts_u32(ad, 0u);
+                        const uint32_t up = v >> a.pack_shift, lowc = (v & lowmask) - up;
+                        if (lowc) atomicAdd(dst + (size_t)w * 32, lowc);
+                        if (up) atomicAdd(dst + (size_t)(w + half) * 32, up);
+                    }
+                }
+            } else {
+                for (int b = 0; b < nbin; b++) {
+                    const uint32_t ad = cb[r] + ((uint32_t)b << 7);
+                    const uint32_t v = lds_u32(ad);
+                    if (v) {
+                        sts_u32(ad, 0u);
+                        atomicAdd(dst + (size_t)b * 32, v);
+                    }
+                }
+            }
+        }
+    };
+    auto one = [&](double t) {
+        double h = 0.0, s6 = 0.0;
+        if (MODE >= 1) {
+            const double tssq = __dmul_rn(t, t);
+            h = __dmul_rn(0.5, tssq);
+            if (MODE >= 2) s6 = __dmul_rn(__dmul_rn(1.0 / 6, tssq), t);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double x = __dmul_rn(t, fN[r]);
+            if (MODE >= 1) x = __dadd_rn(x, __dmul_rn(h, fdN[r]));
+            if (MODE >= 2) x = __dadd_rn(x, __dmul_rn(s6, fddN[r]));
+            const uint32_t lo = (uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC));
+            if (PACKED) red_shared_add_u32((lo & mask) | cb[r], (lo & topbit) | 1u);
+            else red_shared_inc((lo & mask) | cb[r]);
+        }
+    };
+    // plain events [b, e) of a stage: K1's straight-line loop
+    auto span = [&](const unsigned char *tp, int b, int e) {
+        int i = b;
+        if ((i & 1) && i < e) one(*reinterpret_cast<const double *>(tp + (size_t)i * 8)), i++;
+        if (i + UE <= e) {
+            double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8);
+            double2 v1 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8 + 16);
+            for (; i + UE <= e; i += UE) {
+                // next group first (may read the 16-event pad after the stage; unused then)
+                const double2 n0 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8 + 32);
+                const double2 n1 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8 + 48);
+                one(v0.x), one(v0.y), one(v1.x), one(v1.y);
+                v0 = n0, v1 = n1;
+            }
+        }
+        for (; i < e; i++) one(*reinterpret_cast<const double *>(tp + (size_t)i * 8));
+    };
+
+    int row = j0;                      // current row
+    long long row_end = a.row_start[min(j0 + 1, nprof)];
+    int since_drain = 0;
+    for (int it = 0; it < ntiles; it++) {
+        const int buf = it & 1;
+        mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
+        const long long s = es + (long long)it * TILE_EV;
+        const int cnt = (int)min((long long)TILE_EV, ev_hi - s);
+        const unsigned char *tp = smem + a.tile_off + (uint32_t)buf * TILE_BYTES;
+        int e = (int)max(0LL, ev_lo - s);  // only the first stage can start before ev_lo
+        while (e < cnt) {
+            while (s + e >= row_end && row < j1) {  // finished row(s): drain and advance (warp-uniform)
+                if (since_drain) drain(row), since_drain = 0;
+                row++;
+                row_end = a.row_start[min(row + 1, nprof)];
+            }
+            int e_end = (int)min((long long)cnt, row_end - s);
+            if (PACKED) e_end = min(e_end, e + a.flush_events - since_drain);
+            span(tp, e, e_end);
+            since_drain += e_end - e;
+            e = e_end;
+            if (PACKED && since_drain >= a.flush_events) drain(row), since_drain = 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int prev = atomicAdd(&done[buf], 1);
+            if (prev == nwarps - 1) {
+                done[buf] = 0;
+                if (it + 2 < ntiles) {
+                    fence_proxy_async();
+                    issue(it + 2);
+                }
+            }
+        }
+    }
+    if (since_drain) drain(min(row, nprof - 1));
+}
+
+// first event index of every row (binary search; the row index is monotone in t for sorted times)
+__global__ void qffa_rowstart_kernel(const double *__restrict__ t, long long n, double t_first, double delta1, int nprof,
+                                     long long *__restrict__ row_start) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nprof) return;
+    // smallest e with jf(t[e]) >= j   (jf < 0 never happens for sorted t >= t_first)
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const double jf = __dmul_rn(__dsub_rn(t[mid], t_first), delta1);
+        // row of mid: int(jf) if jf < nprof else "dropped" (counts as row nprof)
+        const bool before = (j == nprof) ? (jf < (double)nprof) : (jf < (double)j);
+        if (before) lo = mid + 1;
+        else hi = mid;
+    }
+    row_start[j] = lo;
+}
+
+// flag[0] = 1 if the times are not sorted ascending or not >= t_first
+__global__ void qffa_sorted_kernel(const double *__restrict__ t, long long n, double t_first, int *flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = t[i];
+        if (!(v >= t_first) || (i + 1 < n && t[i + 1] < v)) bad = true;
+    }
+    if (bad) atomicExch(flag, 1);
+}
+
+// [u0, u1) = events with |t| < t_safe (contiguous for sorted times)
+__global__ void qffa_unsafe_range_kernel(const double *__restrict__ t, long long n, double t_safe, long long *out) {
+    if (threadIdx.x > 1 || blockIdx.x > 0) return;
+    const double bound = threadIdx.x == 0 ? -t_safe : t_safe;
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        // u0: first t > -t_safe ; u1: first t >= t_safe
+        const bool before = threadIdx.x == 0 ? (t[mid] <= bound) : (t[mid] < bound);
+        if (before) lo = mid + 1;
+        else hi = mid;
+    }
+    out[threadIdx.x] = lo;
+}
+
+// Re-bin the photons with |t| < t_safe: remove the fast-path bin, add the reference's bin (if any).
+template <int MODE>
+__global__ void __launch_bounds__(128) qffa_fix_kernel(const QLaneArgs a, const long long *__restrict__ urange,
+                                                       double t_first, double delta0, double delta1) {
+    const long long u0 = urange[0], u1 = urange[1];
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= a.n_c) return;
+    const double f = a.f[c], fd = MODE >= 1 ? a.fd[c] : 0.0, fdd = MODE >= 2 ? a.fdd[c] : 0.0;
+    const double fN = __dmul_rn(f, a.scale), fdN = __dmul_rn(fd, a.scale), fddN = __dmul_rn(fdd, a.scale);
+    for (long long e = u0 + blockIdx.x; e < u1; e += gridDim.x) {
+        const double t = a.t[e];
+        const double jf = __dmul_rn(__dsub_rn(t, t_first), delta1);
+        if (!(jf >= 0.0 && jf < (double)a.nprof)) continue;  // was never folded (beyond row_start[nprof])
+        const int j = __double2loint(__dadd_rd(jf, HX_MAGIC));
+        double h = 0.0, s6 = 0.0;
+        if (MODE >= 1) {
+            const double tssq = __dmul_rn(t, t);
+            h = __dmul_rn(0.5, tssq);
+            if (MODE >= 2) s6 = __dmul_rn(__dmul_rn(1.0 / 6, tssq), t);
+        }
+        double x = __dmul_rn(t, fN);
+        if (MODE >= 1) x = __dadd_rn(x, __dmul_rn(h, fdN));
+        if (MODE >= 2) x = __dadd_rn(x, __dmul_rn(s6, fddN));
+        const int fast_bin = (int)(((uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC)) >> 7) & (uint32_t)(a.nbin - 1));
+        const int ref_bin = qffa_bin_generic<MODE>(t, h, s6, f, fd, fdd, delta0, a.nbin);
+        if (ref_bin == fast_bin) continue;
+        uint32_t *p = a.prof + (((size_t)(c >> 5) * a.nprof + j) * a.nbin) * 32 + (c & 31);
+        atomicSub(p + (size_t)fast_bin * 32, 1u);
+        if (ref_bin >= 0) atomicAdd(p + (size_t)ref_bin * 32, 1u);
+    }
+}
+
+// prof_lane [slot][row][bin][32] -> prof [c][row][bin]  (the layout of the public `profiles` output and of K3)
+__global__ void qffa_unlane_kernel(const uint32_t *__restrict__ src, int n_c, int nprof, int nbin,
+                                   uint32_t *__restrict__ dst) {
+    const size_t n = (size_t)n_c * nprof * nbin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / ((size_t)nprof * nbin), rb = i - c * ((size_t)nprof * nbin);
+        dst[i] = src[(((c >> 5) * nprof * (size_t)nbin) + rb) * 32 + (c & 31)];
+    }
+}
+
 // K3, harmonic-domain formulation.  The reference rolls every time slice k by s_k bins, sums the
 // rolled slices (shift_and_sum, efsearch.py:350-363) and takes C_h = sum_b splat[b] cos(2 pi h b/nbin),
 // S_h likewise (ffa.py:98-102).  A circular shift is a rotation of each harmonic:
@@ -421,6 +724,214 @@ static int g_qev_used = 0;
 static long long g_qev_batches = 0;
 static double g_q_last_ms = -1.0;
 
+
+// ---- K2-lane host path -----------------------------------------------------------------------
+typedef void (*qlane_fn_t)(const QLaneArgs);
+template <int R, bool PACKED>
+static qlane_fn_t pick_qlane_m(int mode) {
+    return mode == 0 ? qffa_lane_kernel<R, 0, PACKED> : mode == 1 ? qffa_lane_kernel<R, 1, PACKED> : qffa_lane_kernel<R, 2, PACKED>;
+}
+static qlane_fn_t pick_qlane(int R, int mode, bool packed) {
+    if (packed) return R == 4 ? pick_qlane_m<4, true>(mode) : R == 2 ? pick_qlane_m<2, true>(mode) : pick_qlane_m<1, true>(mode);
+    return R == 4 ? pick_qlane_m<4, false>(mode) : R == 2 ? pick_qlane_m<2, false>(mode) : pick_qlane_m<1, false>(mode);
+}
+
+static int g_qffa_lane = 1;  // tuning hook: 0 forces the lane = event kernel
+
+constexpr int QL_TILE = 1024;
+
+// returns HX_OK, an error (< 0), or 1 when the inputs are not eligible (caller falls back to the lane = event path)
+static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev, double t_first, double t_last,
+                          const double *mean_f, const double *mean_fd, const double *mean_fdd, int64_t n_centres,
+                          int nbin, int nprof, double delta0, double delta1, const double *d_L, const double *d_Q,
+                          int64_t n_lq, const double *d_base, const double *d_tab, int nharm, double *d_stats,
+                          uint32_t *d_profiles, cudaStream_t st, int transient_levels) {
+    const bool p2 = (nbin & (nbin - 1)) == 0;
+    if (!g_qffa_lane || !g_qffa_fast || !p2 || nbin < 8 || nbin > 512 || n_centres < 1) return 1;
+    int mode = 0;
+    double fmin = INFINITY, fmax = 0.0, fdabs = 0.0, fddabs = 0.0;
+    for (int64_t c = 0; c < n_centres; c++) {
+        if (mean_fdd[c] != 0) mode = 2;
+        else if (mean_fd[c] != 0) mode = std::max(mode, 1);
+        fmin = std::min(fmin, mean_f[c]);
+        fmax = std::max(fmax, std::fabs(mean_f[c]));
+        fdabs = std::max(fdabs, std::fabs(mean_fd[c]));
+        fddabs = std::max(fddabs, std::fabs(mean_fdd[c]));
+    }
+    if (!(fmin > 0) || !std::isfinite(fmin)) return 1;
+    const double tmax = std::max(std::fabs(t_first), std::fabs(t_last));
+    const double t_safe = 1.0 / fmin;
+    auto g = [&](double x) { return x * fmin - 0.5 * x * x * fdabs - x * x * x * fddabs / 6; };
+    const double scale = (double)nbin * 128.0;
+    const double phmax = tmax * fmax + 0.5 * tmax * tmax * fdabs + tmax * tmax * tmax * fddabs / 6;
+    if (!(g(t_safe) >= 0.75 && (tmax <= t_safe || g(tmax) >= 0.75) && phmax * scale < 1125899906842624.0)) return 1;
+
+    // ---- once per call: sortedness, row boundaries, the |t| < t_safe range, centre constants on the device
+    void *d_misc = nullptr, *d_cent = nullptr, *d_lane = nullptr, *d_plain = nullptr, *d_coef = nullptr;
+    struct Free {
+        void *&p;
+        cudaStream_t s;
+        ~Free() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } f1{d_misc, st}, f2{d_cent, st}, f3{d_lane, st}, f4{d_plain, st}, f5{d_coef, st};
+    const size_t misc_bytes = (size_t)(nprof + 1 + 2) * 8 + 16;
+    HX_CUDA_TRY(cudaMallocAsync(&d_misc, misc_bytes, st));
+    HX_CUDA_TRY(cudaMemsetAsync(d_misc, 0, misc_bytes, st));
+    long long *d_rowstart = reinterpret_cast<long long *>(d_misc), *d_urange = d_rowstart + nprof + 1;
+    int *d_flags = reinterpret_cast<int *>(d_urange + 2);  // [0] unsorted, [1] layout error
+    qffa_sorted_kernel<<<(unsigned)std::min<long long>((n_ev + 255) / 256, 2368), 256, 0, st>>>(d_t, n_ev, t_first, d_flags);
+    HX_CHECK_LAUNCH("qffa_sorted_kernel");
+    qffa_rowstart_kernel<<<(nprof + 1 + 127) / 128, 128, 0, st>>>(d_t, n_ev, t_first, delta1, nprof, d_rowstart);
+    HX_CHECK_LAUNCH("qffa_rowstart_kernel");
+    qffa_unsafe_range_kernel<<<1, 32, 0, st>>>(d_t, n_ev, t_safe, d_urange);
+    HX_CHECK_LAUNCH("qffa_unsafe_range_kernel");
+    int h_flags[2] = {0, 0};
+    long long h_urange[2] = {0, 0};
+    HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaMemcpyAsync(h_urange, d_urange, 16, cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_flags[0]) return 1;  // unsorted input: the lane = event kernel copes with it
+    const long long n_unsafe = std::max<long long>(0, h_urange[1] - h_urange[0]);
+
+    std::vector<double> hc(3 * (size_t)n_centres);
+    for (int64_t c = 0; c < n_centres; c++) hc[c] = mean_f[c], hc[n_centres + c] = mean_fd[c], hc[2 * n_centres + c] = mean_fdd[c];
+    HX_CUDA_TRY(cudaMallocAsync(&d_cent, hc.size() * 8, st));
+    HX_CUDA_TRY(cudaMemcpyAsync(d_cent, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st));
+    const double *d_f = reinterpret_cast<double *>(d_cent), *d_fd = d_f + n_centres, *d_fdd = d_fd + n_centres;
+
+    // ---- kernel configuration (same footprint classes as K1)
+    const bool packed = nbin >= 128;
+    const int foot = packed ? nbin / 2 : nbin;
+    int R = foot <= 32 ? 4 : foot <= 64 ? 2 : 1;
+    if (mode >= 1 && R == 4 && foot > 16) R = 2;
+    int W = foot <= 16 ? 8 : 4;
+    // batches of equal size (multiples of 32 centres), bounded by 512 MiB of profile scratch
+    const size_t per_centre = (size_t)nprof * nbin * 4;
+    const int64_t cap = std::max<int64_t>(32, (int64_t)(((size_t)512 << 20) / per_centre) / 32 * 32);
+    const int64_t n_batches = (n_centres + cap - 1) / cap;
+    const int cb_max = (int)std::min<int64_t>(((n_centres + n_batches - 1) / n_batches + 31) / 32 * 32, n_centres + 31);
+    const int slots_max = (cb_max + 31) / 32;
+    while (R > 1 && R > slots_max) R /= 2;  // small batches: no idle trial slots
+    {
+        // CTA columns: as few as possible, each with just enough warps for its share of the slots
+        const int gx = (slots_max + R * W - 1) / (R * W);
+        W = std::max(1, (slots_max + R * gx - 1) / (R * gx));
+    }
+    const uint32_t blk = (uint32_t)nbin * (packed ? 64u : 128u);
+    uint32_t hist_off, tile_off, total;
+    int tile_ev = QL_TILE;
+    for (;;) {
+        const uint32_t hist_bytes = (uint32_t)W * R * blk;
+        const uint32_t hist_abs = (di.dyn_smem_base + 32 + blk - 1) / blk * blk;
+        hist_off = hist_abs - di.dyn_smem_base;
+        const uint32_t gap = hist_off - 32;
+        int fit = 0;  // largest stage that fits in the alignment gap in front of the histograms
+        for (int t = QL_TILE; t >= 256; t -= 64)
+            if (2u * (uint32_t)(t + 16) * 8u <= gap) {
+                fit = t;
+                break;
+            }
+        tile_ev = fit ? fit : QL_TILE;
+        const uint32_t tile_region = 2u * (uint32_t)(tile_ev + 16) * 8u;
+        tile_off = fit ? 32u : hist_off + hist_bytes;
+        total = std::max(hist_off + hist_bytes, tile_off + tile_region);
+        if (total <= (uint32_t)di.smem_optin) break;
+        if (W > 1) W /= 2;
+        else if (R > 1) R /= 2;
+        else return 1;
+    }
+    const int ctas_per_sm = std::max(1, std::min(8, (int)(di.smem_per_sm / (total + di.reserved_smem))));
+    qlane_fn_t fn = pick_qlane(R, mode, packed);
+    HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+
+    const size_t lane_elems = (size_t)slots_max * nprof * nbin * 32;
+    const size_t prof_elems = (size_t)nprof * nbin;
+    HX_CUDA_TRY(cudaMallocAsync(&d_lane, lane_elems * 4, st));
+    if (!d_profiles) HX_CUDA_TRY(cudaMallocAsync(&d_plain, (size_t)cb_max * prof_elems * 4, st));
+    const size_t coef_elems = (size_t)cb_max * nprof * nharm * 2;
+    HX_CUDA_TRY(cudaMallocAsync(&d_coef, coef_elems * 8 + (size_t)cb_max * 8 + (size_t)cb_max * nprof * 8, st));
+    unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(d_coef) + coef_elems);
+    unsigned long long *d_rowcnt = d_tot + cb_max;
+    const size_t step_smem = (2 * (size_t)nbin + 16) * sizeof(double);
+
+    g_qev_used = 0, g_qev_batches = 0, g_q_last_ms = -1.0;
+    for (int64_t c0 = 0; c0 < n_centres; c0 += cb_max) {
+        const int C = (int)std::min<int64_t>(cb_max, n_centres - c0);
+        const int slots = (C + 31) / 32;
+        HX_CUDA_TRY(cudaMemsetAsync(d_lane, 0, (size_t)slots * nprof * nbin * 32 * 4, st));
+        QLaneArgs a{};
+        a.t = d_t, a.n_ev = n_ev, a.row_start = d_rowstart;
+        a.f = d_f + c0, a.fd = d_fd + c0, a.fdd = d_fdd + c0, a.n_c = C;
+        a.nbin = nbin, a.nprof = nprof, a.scale = scale;
+        int log2nbin = 0;
+        while ((1 << log2nbin) < nbin) log2nbin++;
+        a.pack_shift = 6 + log2nbin, a.topbit = 1u << a.pack_shift;
+        a.binmask = packed ? (uint32_t)(nbin / 2 - 1) << 7 : (uint32_t)(nbin - 1) << 7;
+        a.flush_events = (int)((1u << a.pack_shift) - 1u);
+        a.prof = reinterpret_cast<uint32_t *>(d_lane);
+        a.warps = W, a.hist_off = hist_off, a.tile_off = tile_off, a.tile_ev = tile_ev, a.errflag = d_flags + 1;
+        const int grid_x = (slots + R * W - 1) / (R * W);
+        const long long want_y = std::max<long long>(1, 4LL * di.sm_count * ctas_per_sm / grid_x);
+        long long per = std::max<long long>((n_ev + want_y - 1) / want_y, 4LL * tile_ev);
+        per = (per + 1) & ~1LL;
+        a.ev_per_cta = per;
+        const int grid_y = (int)std::min<long long>(65535, (n_ev + per - 1) / per);
+        if ((long long)grid_y * per < n_ev) a.ev_per_cta = ((n_ev + grid_y - 1) / grid_y + 1) & ~1LL;
+        const bool timed = g_qev_ok && g_qev_used < QF_EVPOOL;
+        if (timed) HX_CUDA_TRY(cudaEventRecord(g_qev[2 * g_qev_used], st));
+        fn<<<dim3((unsigned)grid_x, (unsigned)grid_y), W * 32, total, st>>>(a);
+        HX_CHECK_LAUNCH("qffa_lane_kernel");
+        if (timed) {
+            HX_CUDA_TRY(cudaEventRecord(g_qev[2 * g_qev_used + 1], st));
+            g_qev_used++;
+        }
+        g_qev_batches++;
+        if (n_unsafe > 0) {
+            dim3 gf((unsigned)std::min<long long>(n_unsafe, 256), (unsigned)((C + 127) / 128));
+            if (mode == 0) qffa_fix_kernel<0><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            else if (mode == 1) qffa_fix_kernel<1><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            else qffa_fix_kernel<2><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            HX_CHECK_LAUNCH("qffa_fix_kernel");
+        }
+        uint32_t *prof = d_profiles ? d_profiles + (size_t)c0 * prof_elems : reinterpret_cast<uint32_t *>(d_plain);
+        qffa_unlane_kernel<<<di.sm_count * 8, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin, prof);
+        HX_CHECK_LAUNCH("qffa_unlane_kernel");
+        HX_CUDA_TRY(cudaMemsetAsync(d_tot, 0, (size_t)cb_max * 8, st));
+        dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)C);
+        qffa_rowdft_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
+            prof, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
+            transient_levels > 0 ? d_rowcnt : nullptr);
+        HX_CHECK_LAUNCH("qffa_rowdft_kernel");
+        if (transient_levels > 0) {
+            dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
+            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, nharm,
+                                                       transient_levels, d_stats + (size_t)c0 * transient_levels * nprof);
+            HX_CHECK_LAUNCH("qffa_transient_kernel");
+        } else {
+            dim3 g2((unsigned)n_lq, (unsigned)C);
+            qffa_step_kernel<<<g2, 256, step_smem, st>>>(reinterpret_cast<double *>(d_coef), d_tot, nprof, nbin, d_L, d_Q,
+                                                          (int)n_lq, d_base, d_tab, nharm, d_stats + (size_t)c0 * n_lq);
+            HX_CHECK_LAUNCH("qffa_step_kernel");
+        }
+    }
+    HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_flags[1]) {
+        set_error("qffa_lane_kernel: shared-memory layout mismatch");
+        return HX_ERR_INTERNAL;
+    }
+    if (g_qev_used > 0) {
+        double sum = 0.0;
+        for (int i = 0; i < g_qev_used; i++) {
+            float fms = 0.f;
+            if (cudaEventElapsedTime(&fms, g_qev[2 * i], g_qev[2 * i + 1]) == cudaSuccess) sum += fms;
+        }
+        g_q_last_ms = sum * (double)g_qev_batches / (double)g_qev_used;
+    }
+    return HX_OK;
+}
+
 // transient_levels > 0: instead of the (L, Q) shift search, write the sub-interval statistics of the
 // transient search, d_stats[n_centres][transient_levels][nprof]
 int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double t_last, const double *mean_f,
@@ -486,6 +997,18 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
     HX_CUDA_TRY(cudaMemcpyAsync(d_const, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     const double *d_base = reinterpret_cast<double *>(d_const), *d_tab = d_base + nprof, *d_L = d_tab + 2 * nbin,
                  *d_Q = d_L + n_lq;
+    if (!g_qev_ok) {
+        bool ok = true;
+        for (int i = 0; i < 2 * QF_EVPOOL && ok; i++) ok = cudaEventCreate(&g_qev[i]) == cudaSuccess;
+        g_qev_ok = ok;
+    }
+    {
+        // preferred path: lane = centre (conflict-free atomics); falls through when not eligible
+        int rl = qffa_lane_path(di, d_t, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin, nprof,
+                                delta0, delta1, d_L, d_Q, n_lq, d_base, d_tab, nharm, d_stats, d_profiles, st,
+                                transient_levels);
+        if (rl <= 0) return rl;
+    }
     const size_t prof_elems = (size_t)nprof * nbin;
     if (!d_profiles) HX_CUDA_TRY(cudaMallocAsync(&d_scratch, prof_elems * cmax * sizeof(uint32_t), st));
 
@@ -642,6 +1165,9 @@ int hx_qffa_last_kernel_ms(double *ms, int64_t *launches) {
 
 int hx_qffa_set_tuning(int cmax) {
     // cmax in [1, 8]: centres per pass; +100 additionally disables the power-of-two fast phase path
+    // +1000: additionally force the lane = event kernel (disable the lane = centre path)
+    hx::g_qffa_lane = cmax >= 1000 ? 0 : 1;
+    if (cmax >= 1000) cmax -= 1000;
     hx::g_qffa_fast = cmax >= 100 ? 0 : 1;
     if (cmax >= 100) cmax -= 100;
     hx::g_qffa_cmax = (cmax >= 1 && cmax <= hx::QF_CMAX) ? cmax : hx::QF_CMAX;

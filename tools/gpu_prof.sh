@@ -1,10 +1,7 @@
 #!/bin/bash
-# ncu captures of the K1 kernel on the two bench shapes (reduced event counts: ncu replays ~40x)
+# ncu capture of K1 on the nbin=128 f-only shape (C1/C5 class)
 mkdir -p gpurun_out
-A="300000 2048 64 128 4"       # C3 shape (f, fdot), nbin=128 -> packed counters
-B="300000 400000 1 16 0"       # C2 shape, f only, nbin=16
+A="400000 262144 1 128 2"
 python tools/prof_fold.py $A > gpurun_out/plain_a.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fold_kernel -s 1 -c 1 -o gpurun_out/fold_c3 -f python tools/prof_fold.py $A > gpurun_out/ncu_a.log 2>&1
-python tools/prof_fold.py $B > gpurun_out/plain_b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fold_kernel -s 1 -c 1 -o gpurun_out/fold_c2 -f python tools/prof_fold.py $B > gpurun_out/ncu_b.log 2>&1
-tail -n 3 gpurun_out/ncu_a.log gpurun_out/ncu_b.log
+ncu --set full --clock-control none --import-source on -k regex:fold_kernel -s 1 -c 1 -o gpurun_out/fold_n128f -f python tools/prof_fold.py $A > gpurun_out/ncu_a.log 2>&1
+tail -n 2 gpurun_out/ncu_a.log

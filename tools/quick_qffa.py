@@ -17,9 +17,9 @@ for nbin, n in ((128, 2), (16, 1)):
     nprof = 16 * nbin
     for sfd in (True, False):
         L, Q = _shift_grids(nbin, 2, 8 if n == 2 else 8, sfd)
-        for cmax in (1, 2, 4, 8):
+        for cmax in (1008, 8):
             lib.hx_qffa_set_tuning(cmax)
-            _qffa_device_call(td, ts[0], ts[-1], cents[:8], nbin, nprof, L, Q, n)
+            _qffa_device_call(td, ts[0], ts[-1], cents, nbin, nprof, L, Q, n)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             _qffa_device_call(td, ts[0], ts[-1], cents, nbin, nprof, L, Q, n)
@@ -28,5 +28,5 @@ for nbin, n in ((128, 2), (16, 1)):
             per = dt / len(cents)
             print(f"N={n_ev:.0e} nbin={nbin} n={n} nLQ={L.size} cmax={cmax}: {per*1e6:8.1f} us/centre "
                   f"=> event-bytes {8*n_ev/per/1e9:8.1f} GB/s-equivalent per centre, "
-                  f"{8*n_ev/(per*cmax)/1e9:7.1f} GB/s actually streamed", flush=True)
+                  f"K2 kernels {_cabi.qffa_last_kernel()[0]/len(cents)*1e3:7.1f} us/centre ({'lane=event' if cmax >= 1000 else 'lane=centre'})", flush=True)
 lib.hx_qffa_set_tuning(0)
