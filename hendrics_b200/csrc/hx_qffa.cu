@@ -655,6 +655,115 @@ __global__ void __launch_bounds__(256) qffa_step_kernel(const double *__restrict
     if (threadIdx.x == 0) stats[(size_t)c * n_lq + lq] = 2.0 / (double)tot[c] * res;
 }
 
+
+// (a') the same coefficients straight from the lane layout prof[slot][row][bin][32]: one warp per
+// (slot, row), lane = centre, so every load is one coalesced 128-byte line and nothing is reduced
+// across lanes.  Replaces qffa_unlane_kernel + qffa_rowdft_kernel on the lane = centre path.
+__global__ void __launch_bounds__(256) qffa_rowdft_lane_kernel(const uint32_t *__restrict__ prof, int n_c, int nprof,
+                                                               int nbin, int nharm, const double *__restrict__ tab,
+                                                               double *__restrict__ coef /*[C][nprof][nharm][2]*/,
+                                                               unsigned long long *__restrict__ tot /*[C]*/,
+                                                               unsigned long long *__restrict__ rowcnt) {
+    extern __shared__ double tsm[];  // cos | sin
+    for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) tsm[i] = tab[i];
+    __syncthreads();
+    const int slot = blockIdx.y, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int c = slot * 32 + lane;
+    if (row >= nprof) return;
+    const uint32_t *p = prof + (((size_t)slot * nprof + row) * nbin) * 32 + lane;
+    const bool p2 = (nbin & (nbin - 1)) == 0;
+    unsigned long long cnt = 0;
+    for (int b = 0; b < nbin; b++) cnt += p[(size_t)b * 32];
+    if (c < n_c) {
+        if (cnt) atomicAdd(&tot[c], cnt);
+        if (rowcnt) rowcnt[(size_t)c * nprof + row] = cnt;
+    }
+    for (int h = 1; h <= nharm; h++) {
+        double cr = 0.0, sr = 0.0;
+        int idx = 0;
+        for (int b = 0; b < nbin; b++) {
+            const double v = (double)p[(size_t)b * 32];
+            cr += tsm[idx] * v;
+            sr += tsm[nbin + idx] * v;
+            idx += h;
+            if (p2) idx &= nbin - 1;
+            else idx %= nbin;
+        }
+        if (c < n_c) {
+            double *d = coef + (((size_t)c * nprof + row) * nharm + (h - 1)) * 2;
+            d[0] = cr, d[1] = sr;
+        }
+    }
+}
+
+// (b') thread = (L, Q) pair: no reduction over threads at all for up to 64 pairs per CTA; the remaining
+// threads of the CTA split the time slices.  NH harmonics are accumulated in registers.
+template <int NH>
+__global__ void __launch_bounds__(256) qffa_step2_kernel(const double *__restrict__ coef,
+                                                         const unsigned long long *__restrict__ tot, int nprof,
+                                                         int nbin, const double *__restrict__ L,
+                                                         const double *__restrict__ Q, int n_lq, int pairs_per_cta,
+                                                         const double *__restrict__ base_shift,
+                                                         const double *__restrict__ tab, double *__restrict__ stats) {
+    extern __shared__ double ssm[];  // cos | sin | partial sums [groups][pairs][2*NH]
+    double *part = ssm + 2 * nbin;
+    for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) ssm[i] = tab[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int groups = blockDim.x / pairs_per_cta;
+    const int pl = threadIdx.x % pairs_per_cta, g = threadIdx.x / pairs_per_cta;
+    const int lq = blockIdx.x * pairs_per_cta + pl;
+    const bool active = lq < n_lq && g < groups;
+    const bool p2 = (nbin & (nbin - 1)) == 0;
+    double cs[NH], sn[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) cs[h] = 0.0, sn[h] = 0.0;
+    if (active) {
+        const double l = L[lq], q = Q[lq];
+        for (int k = g; k < nprof; k += groups) {
+            const double b = base_shift[k];
+            const double tot_shift = __dadd_rn(__dmul_rn(b, l), __dmul_rn(__dmul_rn(b, b), q));
+            const double r = __dsub_rn(__dadd_rn(tot_shift, HX_MAGIC), HX_MAGIC);  // np.rint: half to even
+            int s = (int)r;
+            s = p2 ? (s & (nbin - 1)) : ((s % nbin) + nbin) % nbin;  // np.mod -> [0, nbin)
+            const double2 *d = reinterpret_cast<const double2 *>(coef + ((size_t)c * nprof + k) * NH * 2);
+            int idx = 0;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                idx += s;
+                if (p2) idx &= nbin - 1;
+                else idx %= nbin;
+                const double ct = ssm[idx], st = ssm[nbin + idx];
+                const double2 v = d[h];  // (Cr, Sr): the same address for every pair of a group: broadcast
+                cs[h] += v.x * ct - v.y * st;
+                sn[h] += v.y * ct + v.x * st;
+            }
+        }
+    }
+    if (g < groups) {
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+            part[((size_t)g * pairs_per_cta + pl) * 2 * NH + 2 * h] = cs[h];
+            part[((size_t)g * pairs_per_cta + pl) * 2 * NH + 2 * h + 1] = sn[h];
+        }
+    }
+    __syncthreads();
+    if (g == 0 && lq < n_lq) {
+        double res = 0.0;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+            double a = 0.0, bsum = 0.0;
+            for (int gg = 0; gg < groups; gg++) {
+                a += part[((size_t)gg * pairs_per_cta + pl) * 2 * NH + 2 * h];
+                bsum += part[((size_t)gg * pairs_per_cta + pl) * 2 * NH + 2 * h + 1];
+            }
+            res += a * a + bsum * bsum;
+        }
+        stats[(size_t)c * n_lq + lq] = 2.0 / (double)tot[c] * res;
+    }
+}
+
 // Transient search (hendrics/efsearch.py:407-465, _average_and_z_sub_search): for every averaging level
 // l (groups of 2^l consecutive time slices) the Z^2_n of the summed sub-profiles, written to all rows of
 // the group.  Sums of profiles are sums of their harmonic coefficients, so no profile is touched again.
@@ -848,7 +957,6 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     const size_t lane_elems = (size_t)slots_max * nprof * nbin * 32;
     const size_t prof_elems = (size_t)nprof * nbin;
     HX_CUDA_TRY(cudaMallocAsync(&d_lane, lane_elems * 4, st));
-    if (!d_profiles) HX_CUDA_TRY(cudaMallocAsync(&d_plain, (size_t)cb_max * prof_elems * 4, st));
     const size_t coef_elems = (size_t)cb_max * nprof * nharm * 2;
     HX_CUDA_TRY(cudaMallocAsync(&d_coef, coef_elems * 8 + (size_t)cb_max * 8 + (size_t)cb_max * nprof * 8, st));
     unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(d_coef) + coef_elems);
@@ -894,20 +1002,35 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
             else qffa_fix_kernel<2><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
             HX_CHECK_LAUNCH("qffa_fix_kernel");
         }
-        uint32_t *prof = d_profiles ? d_profiles + (size_t)c0 * prof_elems : reinterpret_cast<uint32_t *>(d_plain);
-        qffa_unlane_kernel<<<di.sm_count * 8, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin, prof);
-        HX_CHECK_LAUNCH("qffa_unlane_kernel");
+        if (d_profiles) {
+            qffa_unlane_kernel<<<di.sm_count * 8, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin,
+                                                                 d_profiles + (size_t)c0 * prof_elems);
+            HX_CHECK_LAUNCH("qffa_unlane_kernel");
+        }
         HX_CUDA_TRY(cudaMemsetAsync(d_tot, 0, (size_t)cb_max * 8, st));
-        dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)C);
-        qffa_rowdft_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
-            prof, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
+        dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)slots);
+        qffa_rowdft_lane_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
+            reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
             transient_levels > 0 ? d_rowcnt : nullptr);
-        HX_CHECK_LAUNCH("qffa_rowdft_kernel");
+        HX_CHECK_LAUNCH("qffa_rowdft_lane_kernel");
         if (transient_levels > 0) {
             dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
             qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, nharm,
                                                        transient_levels, d_stats + (size_t)c0 * transient_levels * nprof);
             HX_CHECK_LAUNCH("qffa_transient_kernel");
+        } else if (nharm <= 4) {
+            const int ppc = (int)std::min<int64_t>(64, n_lq);  // pairs per CTA; 256/ppc groups of time slices
+            const int groups = 256 / ppc;
+            const size_t sm2 = (2 * (size_t)nbin + (size_t)groups * ppc * 2 * nharm) * sizeof(double);
+            dim3 g2((unsigned)((n_lq + ppc - 1) / ppc), (unsigned)C);
+            double *coefp = reinterpret_cast<double *>(d_coef), *outp = d_stats + (size_t)c0 * n_lq;
+            switch (nharm) {
+                case 1: qffa_step2_kernel<1><<<g2, 256, sm2, st>>>(coefp, d_tot, nprof, nbin, d_L, d_Q, (int)n_lq, ppc, d_base, d_tab, outp); break;
+                case 2: qffa_step2_kernel<2><<<g2, 256, sm2, st>>>(coefp, d_tot, nprof, nbin, d_L, d_Q, (int)n_lq, ppc, d_base, d_tab, outp); break;
+                case 3: qffa_step2_kernel<3><<<g2, 256, sm2, st>>>(coefp, d_tot, nprof, nbin, d_L, d_Q, (int)n_lq, ppc, d_base, d_tab, outp); break;
+                default: qffa_step2_kernel<4><<<g2, 256, sm2, st>>>(coefp, d_tot, nprof, nbin, d_L, d_Q, (int)n_lq, ppc, d_base, d_tab, outp); break;
+            }
+            HX_CHECK_LAUNCH("qffa_step2_kernel");
         } else {
             dim3 g2((unsigned)n_lq, (unsigned)C);
             qffa_step_kernel<<<g2, 256, step_smem, st>>>(reinterpret_cast<double *>(d_coef), d_tot, nprof, nbin, d_L, d_Q,
