@@ -101,3 +101,57 @@ def test_search_with_qffa_api():
     assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1])
     assert np.array_equal(g[3].astype(np.uint64), r[3])
     np.testing.assert_allclose(g[2], r[2], rtol=RTOL)
+
+
+def test_lane_centre_kernel_equals_lane_event_kernel():
+    """The two K2 implementations (lane = centre, default; lane = event, fallback) give identical 2-D
+    profiles; also with many centres (several warp slots, ragged last slot) and a non-zero fdot/fddot."""
+    from hendrics_b200 import _cabi
+
+    ts = _centred(60000, 3000.0, seed=77)
+    lin = np.linspace(-64, 64, 8)
+    L, Q = np.meshgrid(lin, lin, indexing="ij")
+    lib = _cabi.lib()
+    for nbin, nprof, mode in ((32, 256, 0), (128, 512, 1), (16, 128, 2)):
+        cents = [(9.7 + 0.003 * i, 0.0 if mode == 0 else 2e-8 * (i % 5 - 2), 0.0 if mode < 2 else 3e-12) for i in range(75)]
+        try:
+            lib.hx_qffa_set_tuning(0)
+            s_lane, p_lane = _host_qffa(ts, cents, nbin, nprof, L, Q, 2)
+            lib.hx_qffa_set_tuning(1008)
+            s_ev, p_ev = _host_qffa(ts, cents, nbin, nprof, L, Q, 2)
+        finally:
+            lib.hx_qffa_set_tuning(0)
+        assert np.array_equal(p_lane, p_ev), (nbin, nprof, mode)
+        np.testing.assert_allclose(s_lane, s_ev, rtol=1e-11)
+        ref_p = C.qffa_profiles(ts, *cents[37], nbin, nprof)
+        assert np.array_equal(p_lane[37].astype(np.uint64), ref_p)
+
+
+def test_qffa_unsorted_times_fall_back_and_stay_exact():
+    """Unsorted input: the reference still histograms every photon (only its range uses t[0], t[-1]);
+    the lane = centre path detects it on the device and the lane = event kernel takes over."""
+    rng = np.random.default_rng(8)
+    ts = _centred(20000, 1000.0, seed=5)
+    perm = rng.permutation(ts.size - 2) + 1
+    tu = np.concatenate([ts[:1], ts[perm], ts[-1:]])  # keep first/last so that the range is unchanged
+    lin = np.linspace(-32, 32, 8)
+    L, Q = np.meshgrid(lin, lin, indexing="ij")
+    stats, prof = _host_qffa(tu, [(9.9, 0, 0), (9.91, 1e-7, 0)], 16, 128, L, Q, 2)
+    for ic, c in enumerate([(9.9, 0, 0), (9.91, 1e-7, 0)]):
+        ref_p = C.qffa_profiles(tu, *c, 16, 128)
+        assert np.array_equal(prof[ic].astype(np.uint64), ref_p)
+        np.testing.assert_allclose(stats[ic], C.fast_step(ref_p, L, Q, 2), rtol=RTOL)
+
+
+def test_qffa_photons_near_t0_are_fixed_up():
+    """Photons with |t| < 1/f_min take the reference's rounding (phase - floor(phase) is inexact there):
+    put many photons inside that window and compare with the oracle, several centres."""
+    rng = np.random.default_rng(9)
+    ts = np.sort(np.concatenate([rng.uniform(-500, 500, 20000), rng.uniform(-0.4, 0.4, 3000)]))
+    cents = [(2.5 + 0.01 * i, -1e-7 * i, 0.0) for i in range(40)]
+    lin = np.linspace(-32, 32, 4)
+    L, Q = np.meshgrid(lin, lin, indexing="ij")
+    stats, prof = _host_qffa(ts, cents, 64, 128, L, Q, 2)
+    for ic in (0, 13, 39):
+        ref_p = C.qffa_profiles(ts, *cents[ic], 64, 128)
+        assert np.array_equal(prof[ic].astype(np.uint64), ref_p), ic
