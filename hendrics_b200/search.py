@@ -18,7 +18,15 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "z_n_search_unbinned"]
+__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "z_n_search_unbinned", "UPSTREAM_SEMANTICS"]
+
+# The two places where the restatement of stingray's `_folding_search` could not be checked against
+# its source.  A maintainer with stingray at hand can flip
+# them without touching any kernel; the oracle has the same switches.
+UPSTREAM_SEMANTICS = {
+    "rezero_to_first_event": True,  # A1: times -= times[0] before folding
+    "drop_last_event": True,        # A2: segment mask is [s, s + segment_size): t == t[-1] is not folded
+}
 
 
 def _torch():
@@ -89,18 +97,22 @@ def _folding_search(
     times = np.asanyarray(times)
     if times.size == 0:
         raise ValueError("No events to fold")
+    rezero = UPSTREAM_SEMANTICS["rezero_to_first_event"]
     if times.dtype == np.float64:
         # A1: re-zero to the first event.  The fp64 subtraction is done on the device (same IEEE
         # operation as numpy's) to spare two host passes over the event list.
-        length = np.float64(times[-1] - times[0])
-        times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev) - float(times[0])
+        t_first = np.float64(times[0] - times[0]) if rezero else np.float64(times[0])
+        length = np.float64(times[-1] - times[0]) if rezero else np.float64(times[-1])
+        times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
+        if rezero:
+            times_d = times_d - float(times[0])
     else:  # e.g. long double mission times: subtract in the input precision, then cast (efsearch.py:1154)
-        times = (times - times[0]).astype(np.float64)
-        length = times[-1]
+        times = ((times - times[0]) if rezero else times).astype(np.float64)
+        t_first, length = times[0], times[-1]
         times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
     if length < segment_size:
         segment_size = length
-    start_times = np.arange(0.0, length, segment_size)
+    start_times = np.arange(t_first, length, segment_size)
 
     freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
     fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
@@ -108,7 +120,10 @@ def _folding_search(
     prof_d = torch.zeros(fgrid.shape + (nbin,), dtype=torch.int64, device=dev) if return_profiles else None
     count = 0
     for s in start_times:
-        good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open
+        if UPSTREAM_SEMANTICS["drop_last_event"]:
+            good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open
+        else:
+            good = (times_d >= s) & (times_d <= s + segment_size)
         ts_d = times_d[good]
         n_good = ts_d.numel()
         if n_good < 1:

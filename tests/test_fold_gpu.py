@@ -246,3 +246,22 @@ def test_gpu_topk_in_find_peaks():
     assert np.array_equal(got, O.find_peaks_in_image(img, n=7)) or np.array_equal(
         [tuple(g) for g in got], [np.unravel_index(i, img.shape) for i in O.topk_flat(img, 7)[0]])
     assert tuple(got[0]) == (3, 17) and tuple(got[1]) == (40, 19999)
+
+
+def test_upstream_semantics_switches_follow_the_oracle():
+    """A1/A2 (the two unverifiable readings of stingray's _folding_search) can be flipped in the product
+    exactly like in the oracle."""
+    from hendrics_b200 import search, z_n_search
+
+    ts = _events(9000, 400.0, seed=23) + 50.0
+    freqs = np.arange(9.85, 9.95, 0.001)
+    saved = dict(search.UPSTREAM_SEMANTICS)
+    try:
+        for rz in (True, False):
+            for dl in (True, False):
+                search.UPSTREAM_SEMANTICS.update(rezero_to_first_event=rz, drop_last_event=dl)
+                f1, s1 = z_n_search(ts, freqs, nharm=2, nbin=32)
+                f0, s0 = O.z_n_search(ts, freqs, nharm=2, nbin=32, rezero_to_first_event=rz, drop_last_event=dl)
+                np.testing.assert_allclose(s1, s0, rtol=RTOL, err_msg=f"rezero={rz} drop_last={dl}")
+    finally:
+        search.UPSTREAM_SEMANTICS.update(saved)
