@@ -50,8 +50,8 @@ WORKLOADS = {
 
 # C4: HENzsearch --fast (quasi-fast folding): K2 streaming 2-D histogram + K3 shift-and-sum.
 # (description, n_events, T, centres per GPU, f0, f1, nbin, nharm)
-C4 = ("C4: HENzsearch --fast (binned quasi-fast folding + fdot shift search), 1e8 events, nbin=128, N=2, "
-      "nprof=2048, 16x16 (L,Q) shifts, 320 centre frequencies", 100_000_000, 1e5, 320, 9.85, 9.95, 128, 2)
+C4 = ("C4: HENzsearch --fast -f 9.85 -F 9.95 -N 2 -n 128 (binned quasi-fast folding + fdot shift search), 1e8 events, "
+      "nprof=2048, 16x16 (L,Q) shifts, all 1252 centre frequencies of the band", 100_000_000, 1e5, 1252, 9.85, 9.95, 128, 2)
 
 
 def algorithmic_ops_per_evtr(n_fd_nonzero):
@@ -181,8 +181,9 @@ def c4_inputs(rank, world):
     desc, n_ev, T, ncent, f0, f1, nbin, n = C4
     times = simulate_events(n_ev, T, seed=4, amp=0.0 if n_ev > 20_000_000 else 0.25)  # thinning 1e8 events is slow; uniform
     tc = times - (times.max() + times.min()) / 2
-    cents, _ = qffa_centres(f0, f1, T, 2)
-    cents = np.asarray(cents[rank * ncent:(rank + 1) * ncent] if (rank + 1) * ncent <= len(cents) else cents[:ncent])
+    # weak scaling: rank r searches the band shifted by r * (f1 - f0)
+    cents, _ = qffa_centres(f0 + rank * (f1 - f0), f1 + rank * (f1 - f0), T, 2)
+    cents = np.asarray(cents[:ncent])
     L, Q = _shift_grids(nbin, 2, 4 * n, True)
     return desc, tc, cents, L, Q, nbin, 16 * nbin, n
 
