@@ -33,6 +33,7 @@
 //     RED.ADD and a second small kernel computes the statistics.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -765,7 +766,12 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     }
     // trial batching bounds the global scratch of the non-fused path (1 GiB)
     const size_t scratch_per_tb = (size_t)R * nbin * 32 * sizeof(uint32_t);
-    long long tb_per_batch = std::max<long long>(W, (long long)(((size_t)1 << 30) / scratch_per_tb) / W * W);
+    size_t scratch_cap = (size_t)1 << 30;
+    if (const char *e = getenv("HX_FOLD_SCRATCH_CAP_KB")) {  // testing hook: force several trial batches
+        const long long kb = atoll(e);
+        if (kb > 0) scratch_cap = (size_t)kb << 10;
+    }
+    long long tb_per_batch = std::max<long long>(W, (long long)(scratch_cap / scratch_per_tb) / W * W);
     const bool must_scratch = mode == MODE_PACKED || d_profiles != nullptr || (flags & HX_FOLD_FORCE_SCRATCH);
     const long long n_tb_first = must_scratch ? std::min(n_tb, tb_per_batch) : n_tb;
     const long long n_cta_x = (n_tb_first + W - 1) / W;

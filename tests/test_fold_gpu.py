@@ -265,3 +265,19 @@ def test_upstream_semantics_switches_follow_the_oracle():
                 np.testing.assert_allclose(s1, s0, rtol=RTOL, err_msg=f"rezero={rz} drop_last={dl}")
     finally:
         search.UPSTREAM_SEMANTICS.update(saved)
+
+
+def test_trial_batching_of_the_scratch_path(monkeypatch):
+    """Large trial grids on the scratch path (packed counters, profiles, event splits) are processed in
+    batches bounded by a scratch cap; force a tiny cap so that several batches (and a ragged last one) run."""
+    monkeypatch.setenv("HX_FOLD_SCRATCH_CAP_KB", "256")
+    ts = _events(12000, 600.0, seed=31)
+    freqs = 9.0 + 2.0 * np.arange(1500) / 1500
+    fdots = [0.0, 1e-6, 2e-6]
+    for nbin in (128, 16):
+        ref_s, ref_p = C.fold_search(ts, freqs, fdots, nbin, 2, want_profiles=True)
+        got_s, got_p = _host_call(ts, freqs, fdots, nbin, 2)
+        assert np.array_equal(got_p.astype(np.int64), ref_p)
+        _assert_stats(got_s, ref_s)
+        got_s2, _ = _host_call(ts, freqs, fdots, nbin, 2, want_profiles=False)
+        _assert_stats(got_s2, ref_s)
