@@ -494,6 +494,7 @@ __global__ void minmax_kernel(const double *__restrict__ x, long long n, double 
     double lo = INFINITY, hi = -INFINITY;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double v = x[i];
+        if (v != v) v = INFINITY, lo = -INFINITY;  // NaN: make the range non-finite so that the host rejects it
         lo = fmin(lo, v);
         hi = fmax(hi, v);
     }

@@ -281,3 +281,46 @@ def test_trial_batching_of_the_scratch_path(monkeypatch):
         _assert_stats(got_s, ref_s)
         got_s2, _ = _host_call(ts, freqs, fdots, nbin, 2, want_profiles=False)
         _assert_stats(got_s2, ref_s)
+
+
+def test_randomized_configs_against_oracle():
+    """Fuzz: random sizes, nbin (power of two or not), harmonics, fdot signs, time offsets and flags."""
+    rng = np.random.default_rng(2026)
+    for it in range(40):
+        n_ev = int(rng.integers(1, 6000))
+        T = float(10 ** rng.uniform(0.5, 4))
+        ts = np.sort(rng.uniform(0, T, n_ev)) + (rng.choice([0.0, 3.0, 1e3]))
+        nbin = int(rng.choice([2, 3, 8, 16, 20, 32, 64, 100, 128, 256, 512, 777, 1024]))
+        nharm = int(rng.choice([0, 1, 2, 5]))
+        n_f = int(rng.integers(1, 150))
+        freqs = rng.uniform(0.01, 50) + rng.uniform(1e-6, 1e-2) * np.arange(n_f)
+        n_fd = int(rng.choice([1, 1, 2, 5]))
+        fdots = [0.0] if n_fd == 1 and rng.random() < 0.5 else list(rng.uniform(-1, 1, n_fd) * 10 ** rng.uniform(-9, -4))
+        flags = int(rng.choice([0, 0, 1, 2, 3]))
+        ref_s, ref_p = C.fold_search(ts, freqs, fdots, nbin, nharm, want_profiles=True)
+        want_prof = bool(rng.random() < 0.6)
+        got_s, got_p = _host_call(ts, freqs, fdots, nbin, nharm, flags=flags, want_profiles=want_prof)
+        msg = f"it={it} n_ev={n_ev} T={T:.3g} nbin={nbin} nharm={nharm} n_f={n_f} fdots={fdots} flags={flags}"
+        if want_prof:
+            assert np.array_equal(got_p.astype(np.int64), ref_p), msg
+        good = np.isfinite(ref_s)
+        assert np.array_equal(np.isfinite(got_s), good), msg
+        np.testing.assert_allclose(got_s[good], ref_s[good], rtol=RTOL, atol=1e-9, err_msg=msg)
+
+
+def test_error_paths():
+    from hendrics_b200 import _cabi
+
+    ts = _events(100, 10.0, seed=1)
+    f = np.array([1.0])
+    with pytest.raises(_cabi.HxError, match="bad sizes"):
+        _host_call(ts, f, [0.0], 1, 0)
+    with pytest.raises(_cabi.HxError, match="bad sizes"):
+        _host_call(ts, f, [0.0], 4096, 0)
+    with pytest.raises(_cabi.HxRangeError, match="exceeds the fp64 folding range"):
+        _host_call(ts * 1e12, np.array([1e6]), [0.0], 16, 0)
+    with pytest.raises(_cabi.HxError, match="non-finite"):
+        _host_call(np.array([0.0, np.nan, 1.0]), f, [0.0], 16, 0)
+    # the library stays usable after an error
+    s, _ = _host_call(ts, f, [0.0], 16, 0)
+    assert np.isfinite(s).all()
