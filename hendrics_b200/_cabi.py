@@ -32,6 +32,11 @@ SIGNATURES = {
     "hx_launch_count": (_i64, []),
     "hx_fold_search": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _int, _uint, _c_dp, _c_u32p, _int]),
     "hx_fold_search_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _uint, _vp, _vp, _vp]),
+    "hx_wfold_search": (_int, [_c_dp, _c_dp, _dbl, _i64, _c_dp, _i64, _c_dp, _i64, _int, _int, _c_dp, _i64, _dbl, _dbl,
+                               _c_dp, _c_dp, _int]),
+    "hx_wfold_search_dev": (_int, [_vp, _vp, _dbl, _i64, _vp, _i64, _vp, _i64, _int, _int, _c_dp, _i64, _dbl, _dbl,
+                                   _vp, _vp, _vp]),
+    "hx_wfold_last_kernel_ms": (_int, [_c_dp]),
     "hx_qffa_search": (_int, [_c_dp, _i64, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64, _int, _c_dp,
                               _c_u32p, _int]),
     "hx_qffa_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64,

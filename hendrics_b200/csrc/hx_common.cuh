@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cmath>
+#include <vector>
+
 #include "../../include/hx_search.h"
 
 namespace hx {
@@ -55,6 +58,32 @@ struct DeviceInfo {
 };
 // Cached per device; probes dyn_smem_base with a tiny kernel on first use.
 int get_device_info(int device, DeviceInfo *out);
+
+// stream-ordered temporary, released on scope exit
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t s;
+    explicit AsyncBuf(cudaStream_t st) : s(st) {}
+    ~AsyncBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
+    template <typename T>
+    T *as() {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// cos/sin tables: 2*pi*arange(0, 1, 1/nbin) as hendrics/ffa.py:40,51
+inline void host_tables(int nbin, std::vector<double> &tab) {
+    tab.resize(2 * (size_t)nbin);
+    const double step = 1.0 / nbin;
+    for (int j = 0; j < nbin; j++) {
+        double tw = (M_PI * 2) * (j * step);
+        tab[j] = cos(tw);
+        tab[nbin + j] = sin(tw);
+    }
+}
 
 // ---- device-side PTX helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
@@ -114,6 +143,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// chi^2 / Z^2_n of one profile; `cnt(j)` returns the count of bin j
+template <typename F>
+__device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const double *ctab, const double *stab) {
+    double tot = 0.0;
+    for (int j = 0; j < nbin; j++) tot += (double)cnt(j);
+    if (nharm == 0) {
+        double mean = tot / (double)nbin;
+        double chi = 0.0;
+        for (int j = 0; j < nbin; j++) {
+            double d = (double)cnt(j) - mean;
+            chi += d * d / mean;
+        }
+        return chi;
+    }
+    double res = 0.0;
+    const bool p2 = (nbin & (nbin - 1)) == 0;
+    for (int k = 1; k <= nharm; k++) {
+        double c = 0.0, s = 0.0;
+        int idx = 0;
+        for (int j = 0; j < nbin; j++) {
+            double p = (double)cnt(j);
+            c += ctab[idx] * p;
+            s += stab[idx] * p;
+            idx += k;
+            if (p2)
+                idx &= nbin - 1;
+            else
+                idx %= nbin;
+        }
+        res += c * c + s * s;
+    }
+    return 2.0 / tot * res;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace hx

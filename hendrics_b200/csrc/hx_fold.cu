@@ -133,40 +133,6 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
-// chi^2 / Z^2_n of one profile; `cnt(j)` returns the count of bin j
-template <typename F>
-__device__ __forceinline__ double profile_stat(F cnt, int nbin, int nharm, const double *ctab, const double *stab) {
-    double tot = 0.0;
-    for (int j = 0; j < nbin; j++) tot += (double)cnt(j);
-    if (nharm == 0) {
-        double mean = tot / (double)nbin;
-        double chi = 0.0;
-        for (int j = 0; j < nbin; j++) {
-            double d = (double)cnt(j) - mean;
-            chi += d * d / mean;
-        }
-        return chi;
-    }
-    double res = 0.0;
-    const bool p2 = (nbin & (nbin - 1)) == 0;
-    for (int k = 1; k <= nharm; k++) {
-        double c = 0.0, s = 0.0;
-        int idx = 0;
-        for (int j = 0; j < nbin; j++) {
-            double p = (double)cnt(j);
-            c += ctab[idx] * p;
-            s += stab[idx] * p;
-            idx += k;
-            if (p2)
-                idx &= nbin - 1;
-            else
-                idx %= nbin;
-        }
-        res += c * c + s * s;
-    }
-    return 2.0 / tot * res;
-}
-
 template <bool HAS_FD, int UE, bool EXACT>
 struct EvGroup {
     double t[UE], tt[HAS_FD ? UE : 1], tte[(EXACT && HAS_FD) ? UE : 1], m2[HAS_FD ? UE : 1];
@@ -521,21 +487,6 @@ static double dec_ordered(long long e) {
     return d;
 }
 
-// stream-ordered temporary, released on scope exit
-struct AsyncBuf {
-    void *p = nullptr;
-    cudaStream_t s;
-    explicit AsyncBuf(cudaStream_t st) : s(st) {}
-    ~AsyncBuf() {
-        if (p) cudaFreeAsync(p, s);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
-    template <typename T>
-    T *as() {
-        return reinterpret_cast<T *>(p);
-    }
-};
-
 // ---- host side --------------------------------------------------------------------------------
 
 struct FoldPlan {
@@ -618,17 +569,6 @@ static long long g_last_grid = 0, g_last_block = 0, g_last_smem = 0;
 static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
 static int g_fold_pack_override = -1;  // -1 auto, 0 never, 1 whenever possible
-
-// cos/sin tables: 2*pi*arange(0, 1, 1/nbin) as hendrics/ffa.py:40,51
-static void host_tables(int nbin, std::vector<double> &tab) {
-    tab.resize(2 * (size_t)nbin);
-    const double step = 1.0 / nbin;
-    for (int j = 0; j < nbin; j++) {
-        double tw = (M_PI * 2) * (j * step);
-        tab[j] = cos(tw);
-        tab[nbin + j] = sin(tw);
-    }
-}
 
 int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
                          const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
@@ -811,7 +751,8 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     host_tables(nbin, tab);
     HX_CUDA_TRY(b_tab.alloc(tab.size() * sizeof(double)));
     HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    const size_t sbytes = fused ? 0 : (size_t)std::min(n_tb, tb_per_batch) * scratch_per_tb;
+    // the grid of a batch overhangs it by < W trial blocks (whole CTAs): the scratch is W-padded
+    const size_t sbytes = fused ? 0 : (size_t)((std::min(n_tb, tb_per_batch) + W - 1) / W * W) * scratch_per_tb;
     if (!fused) HX_CUDA_TRY(b_scratch.alloc(sbytes));
     void *d_tab = b_tab.p, *d_scratch = fused ? nullptr : b_scratch.p;
 
@@ -843,7 +784,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     for (long long tb0 = 0; tb0 < n_tb; tb0 += tb_per_batch) {
         const long long n_tb_b = std::min(tb_per_batch, n_tb - tb0);
         const long long grid_x = (n_tb_b + W - 1) / W;
-        if (!fused) HX_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, (size_t)n_tb_b * scratch_per_tb, st));
+        if (!fused) HX_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, (size_t)(grid_x * W) * scratch_per_tb, st));
         a.tb0 = tb0;
         if (tb0 == 0) HX_CUDA_TRY(cudaEventRecord(g_ev0[device], st));
         dim3 grid((unsigned)grid_x, (unsigned)ev_splits);

@@ -697,15 +697,17 @@ def _common_main(args, func):
                 mjdref = events.mjdref
             if args.emin is not None or args.emax is not None:
                 events, elabel = filter_energy(events, args.emin, args.emax)
-        else:
-            raise ValueError(f"{fname}: only event lists can be searched by hendrics_b200")
+        elif ftype != "lc":
+            raise ValueError(f"{fname}: only event lists and light curves can be searched")
 
         if args.fast:
             oversample = assign_value_if_none(args.oversample, 4 * n)
         else:
             oversample = assign_value_if_none(args.oversample, 2)
 
-        if args.transient:
+        if args.transient and ftype == "lc":
+            log.error("Transient search not yet available for light curves")
+        if args.transient and ftype == "events":
             # efsearch.py:1831-1845; the reference renders an animated GIF (matplotlib + imageio, both
             # unavailable here): the arrays it is drawn from are saved instead
             tr = transient_search(

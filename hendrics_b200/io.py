@@ -23,7 +23,8 @@ from .base import find_peaks_in_image, fold_detection_level, z2_n_detection_leve
 
 HEN_FILE_EXTENSION = ".p"
 
-__all__ = ["EFPeriodogram", "EventList", "save_folding", "load_folding", "load_events", "save_events",
+__all__ = ["EFPeriodogram", "EventList", "Lightcurve", "save_folding", "load_folding", "load_events", "save_events",
+           "save_lcurve", "load_lcurve",
            "get_file_type", "search_best_peaks", "HEN_FILE_EXTENSION"]
 
 
@@ -41,6 +42,39 @@ class EventList:
         self.energy = energy
         self.mission = mission
         self.instr = instr
+
+
+class Lightcurve:
+    """Minimal stand-in for ``stingray.Lightcurve``: what ``folding_search`` reads from a light curve
+    (hendrics/efsearch.py:1154-1157): bin ``time``s, ``counts`` per bin (the fold weights), ``gti``."""
+
+    def __init__(self, time=None, counts=None, gti=None, dt=None, mjdref=0, mission="", instr="", **_ignored):
+        self.time = np.asarray(time)
+        self.counts = np.asarray(counts)
+        if self.time.shape != self.counts.shape:
+            raise ValueError("time and counts must have the same shape")
+        if dt is None:
+            dt = np.median(np.diff(self.time)) if self.time.size > 1 else 1.0
+        self.dt = dt
+        if gti is None and self.time.size > 0:
+            gti = np.array([[self.time[0] - dt / 2, self.time[-1] + dt / 2]])
+        self.gti = None if gti is None else np.asarray(gti)
+        self.mjdref = mjdref
+        self.mission = mission
+        self.instr = instr
+
+
+def save_lcurve(lcurve, fname):
+    out = {"time": lcurve.time, "counts": lcurve.counts, "gti": lcurve.gti, "dt": lcurve.dt, "mjdref": lcurve.mjdref,
+           "mission": lcurve.mission, "instr": lcurve.instr, "__sr__class__type__": "Lightcurve"}
+    with open(fname, "wb") as fobj:
+        pickle.dump(out, fobj)
+
+
+def load_lcurve(fname):
+    with open(fname, "rb") as fobj:
+        out = pickle.load(fobj)
+    return Lightcurve(**{k: v for k, v in out.items() if not k.startswith("__")})
 
 
 def save_events(events, fname):
@@ -74,7 +108,7 @@ def load_events(fname):
 
 
 def get_file_type(fname):
-    """("events", EventList) or ("folding", EFPeriodogram) -- the two types this path handles
+    """("events", EventList), ("lc", Lightcurve) or ("folding", EFPeriodogram) -- the types this path handles
     (hendrics/io.py:473-522)."""
     if fname.endswith((".npy", ".npz")):
         return "events", load_events(fname)
@@ -85,8 +119,10 @@ def get_file_type(fname):
         return "folding", load_folding(fname)
     if kind == "EventList":
         return "events", load_events(fname)
-    raise ValueError(f"File format of {fname} not understood (type {kind!r}); light curves and "
-                     "FITS event files are outside the B200 search path")
+    if kind == "Lightcurve":
+        return "lc", load_lcurve(fname)
+    raise ValueError(f"File format of {fname} not understood (type {kind!r}); FITS / netCDF files are "
+                     "outside the B200 search path")
 
 
 def search_best_peaks(x, stat, threshold):

@@ -18,7 +18,8 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "z_n_search_unbinned", "UPSTREAM_SEMANTICS"]
+__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "fold_profiles_weighted", "z_n_search_unbinned",
+           "UPSTREAM_SEMANTICS"]
 
 # The two places where the restatement of stingray's `_folding_search` could not be checked against
 # its source.  A maintainer with stingray at hand can flip
@@ -150,14 +151,121 @@ def _folding_search(
     return out
 
 
-def _check_branch(expocorr, weights, gti, what):
-    if expocorr and gti is None:
-        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
-    if expocorr or isinstance(weights, Iterable):
-        raise NotImplementedError(
-            f"{what}: the exposure-corrected / weighted `fold_events` branch is outside the B200 hot path "
-            "(SURVEY.md section 8f, rank 3); only the unweighted fast branch is implemented."
+def _is_slow_branch(expocorr, weights):
+    """Upstream takes the `fold_events` branch when the exposure correction is asked for or the weights
+    are an array (``expocorr or not HAS_NUMBA or isinstance(weights, Iterable)``)."""
+    return bool(expocorr) or isinstance(weights, Iterable)
+
+
+def wfold_stats_device(ts_d, w_d, unit_weight, freqs_d, fdots_d, nbin, nharm, gti=None, start_time=0.0,
+                       stop_time=0.0, want_profiles=False):
+    """One K1w call on device tensors (``hx_wfold_search_dev``).  ``w_d`` None: every event weighs
+    ``unit_weight``.  ``gti`` (host, (n, 2)) switches the exposure correction on."""
+    torch = _torch()
+    n_f, n_fd = freqs_d.numel(), fdots_d.numel()
+    stats = torch.empty((n_fd, n_f), dtype=torch.float64, device=ts_d.device)
+    prof = torch.empty((n_fd, n_f, nbin), dtype=torch.float64, device=ts_d.device) if want_profiles else None
+    ts_d = _aligned(ts_d.contiguous())
+    if w_d is not None:
+        w_d = _aligned(w_d.contiguous())
+    n_gti = 0
+    gti_p = None
+    if gti is not None:
+        gti = np.ascontiguousarray(gti, dtype=np.float64).reshape(-1, 2)
+        n_gti, gti_p = gti.shape[0], _cabi.dptr(gti)
+    with torch.cuda.device(ts_d.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _cabi.lib().hx_wfold_search_dev(
+            ts_d.data_ptr(), w_d.data_ptr() if w_d is not None else None, float(unit_weight), ts_d.numel(),
+            freqs_d.data_ptr(), n_f, fdots_d.data_ptr(), n_fd, int(nbin), int(nharm), gti_p, n_gti,
+            float(start_time), float(stop_time), stats.data_ptr(), prof.data_ptr() if want_profiles else None, stream,
         )
+    _cabi.check(rc)
+    return (stats, prof) if want_profiles else stats
+
+
+def _folding_search_weighted(
+    nharm, times, frequencies, nbin=128, segment_size=np.inf, fdots=0, expocorr=False, gti=None, weights=1,
+    device=None, return_profiles=False,
+):
+    """Upstream ``_folding_search(..., use_times=True)`` with the per-trial
+    ``fold_events`` + statistic replaced by one K1w launch per segment.  As upstream: times are re-zeroed to
+    the first event (A1), array keywords as long as ``times`` are masked like the events, the GTIs are handed
+    to ``fold_events`` as they come (NOT re-zeroed with the times), ``start_time = ts[0]`` and
+    ``stop_time = ts[-1] + |ts[1] - ts[0]|`` bound the exposure."""
+    torch = _torch()
+    dev = _device(device)
+    frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
+    fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    times = np.asanyarray(times)
+    if times.size == 0:
+        raise ValueError("No events to fold")
+    n_all = times.size
+    if UPSTREAM_SEMANTICS["rezero_to_first_event"]:
+        times = (times - times[0]).astype(np.float64)
+    else:
+        times = times.astype(np.float64)
+    length = times[-1]
+    if length < segment_size:
+        segment_size = length
+    start_times = np.arange(times[0], times[-1], segment_size)
+
+    times_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
+    w_all = None
+    unit_weight = 1.0
+    if isinstance(weights, Iterable):
+        weights = np.asanyarray(weights)
+        if weights.shape != (n_all,):
+            raise ValueError("weights must be a scalar or have one entry per event")
+        w_all = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+    else:
+        unit_weight = float(weights)
+    gti_all = None
+    if expocorr:
+        gti_all = np.asanyarray(gti).astype(np.float64)
+    freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
+    fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
+    stats_d = torch.zeros(fgrid.shape, dtype=torch.float64, device=dev)
+    prof_d = torch.zeros(fgrid.shape + (nbin,), dtype=torch.float64, device=dev) if return_profiles else None
+    count = 0
+    for s in start_times:
+        if UPSTREAM_SEMANTICS["drop_last_event"]:
+            good = (times_d >= s) & (times_d < s + segment_size)
+        else:
+            good = (times_d >= s) & (times_d <= s + segment_size)
+        ts_d = times_d[good]
+        n_good = ts_d.numel()
+        if n_good < 1:
+            continue
+        edge = ts_d[[0, 1, -1] if n_good > 1 else [0, 0, -1]].cpu().numpy()
+        if edge[2] - edge[0] < 0.2 * segment_size:
+            continue
+        if n_good < 2:
+            raise IndexError("fold_events needs at least two events per segment")  # upstream: times[1]
+        g = gti_all
+        if g is not None and len(g) == n_all:  # upstream masks every keyword as long as `times`
+            g = g[good.cpu().numpy()]
+        res = wfold_stats_device(
+            ts_d, w_all[good] if w_all is not None else None, unit_weight, freqs_d, fdots_d, nbin, nharm, gti=g,
+            start_time=edge[0], stop_time=edge[2] + np.abs(edge[1] - edge[0]), want_profiles=return_profiles,
+        )
+        if return_profiles:
+            stats_d += res[0]
+            prof_d += res[1]
+        else:
+            stats_d += res
+        count += 1
+    stats = stats_d.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        stats = stats / count
+    if fgrid.shape[0] == 1:
+        out = (fgrid.flatten(), stats.flatten())
+    else:
+        out = (fgrid, fdgrid, stats)
+    if return_profiles:
+        out = out + (prof_d.cpu().numpy(),)
+    return out
 
 
 def epoch_folding_search(
@@ -166,8 +274,13 @@ def epoch_folding_search(
     """Epoch-folding chi^2 periodogram.  Same call as ``stingray.pulse.search.epoch_folding_search``.
 
     Returns ``(fgrid, stats)`` (1-D) when a single fdot is searched, else
-    ``(fgrid, fdgrid, stats)`` of shape ``(n_fdot, n_freq)``."""
-    _check_branch(expocorr, weights, gti, "epoch_folding_search")
+    ``(fgrid, fdgrid, stats)`` of shape ``(n_fdot, n_freq)``.  ``expocorr`` / array ``weights`` select the
+    weighted kernel K1w, like upstream's ``fold_events`` branch."""
+    if expocorr and gti is None:
+        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    if _is_slow_branch(expocorr, weights):
+        return _folding_search_weighted(0, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots,
+                                        expocorr=expocorr, gti=gti, weights=weights, **kwargs)
     return _folding_search(0, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
 
 
@@ -184,9 +297,13 @@ def z_n_search(
     **kwargs,
 ):
     """Binned Z^2_n periodogram.  Same call as ``stingray.pulse.search.z_n_search``."""
-    _check_branch(expocorr, weights, gti, "z_n_search")
+    if expocorr and gti is None:
+        raise ValueError("To calculate exposure correction, you need to specify the GTIs")
     if nharm < 1:
         raise ValueError("nharm must be >= 1")
+    if _is_slow_branch(expocorr, weights):
+        return _folding_search_weighted(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots,
+                                        expocorr=expocorr, gti=gti, weights=weights, **kwargs)
     return _folding_search(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
 
 
@@ -204,6 +321,29 @@ def fold_profiles(times, frequencies, fdots=0, nbin=128, nharm=0, device=None, f
     fd_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(fdots), dtype=np.float64)).to(dev)
     stats, prof = fold_stats_device(ts_d, f_d, fd_d, nbin, nharm, flags=flags, want_profiles=True)
     return stats.cpu().numpy(), (prof.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+
+
+def fold_profiles_weighted(times, frequencies, fdots=0, nbin=128, nharm=0, weights=1, gti=None, device=None):
+    """Profiles AND statistics of one weighted (K1w) fold over already-selected times, i.e. upstream's
+    ``fold_events(times, f, fd, nbin=, weights=, gti=, expocorr=gti is not None)`` for every trial.
+
+    Returns ``(stats (n_fd, n_f), profiles (n_fd, n_f, nbin) float64)``; used by the parity tests."""
+    torch = _torch()
+    dev = _device(device)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    ts_d = torch.from_numpy(times).to(dev)
+    f_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(frequencies), dtype=np.float64)).to(dev)
+    fd_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(fdots), dtype=np.float64)).to(dev)
+    w_d, unit = None, 1.0
+    if isinstance(weights, Iterable):
+        w_d = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+    else:
+        unit = float(weights)
+    stats, prof = wfold_stats_device(
+        ts_d, w_d, unit, f_d, fd_d, nbin, nharm, gti=gti, start_time=times[0],
+        stop_time=times[-1] + np.abs(times[1] - times[0]), want_profiles=True,
+    )
+    return stats.cpu().numpy(), prof.cpu().numpy()
 
 
 def z_n_search_unbinned(times, frequencies, nharm=2, fdots=0, device=None):

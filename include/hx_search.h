@@ -80,6 +80,31 @@ int hx_fold_search_dev(const double *d_times, int64_t n_ev, const double *d_freq
                        const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
                        uint32_t *d_profiles, void *stream);
 
+/* ---- K1w: weighted / exposure-corrected fold search ------------------------------------------
+ * Replaces the SLOW branch of stingray.pulse.search._folding_search (use_times=True ->
+ * stingray.pulse.pulsar.fold_events per trial), which z_n_search / epoch_folding_search take when
+ * `weights` is an array (light-curve input, hendrics/efsearch.py:1155-1157) or `expocorr` is set
+ * (`--expocorr`, hendrics/efsearch.py:1164-1167).  Per trial: phase = t*f + (0.5*t*t)*fd minus its floor,
+ * weighted histogram on the edges linspace(0, 1, nbin + 1) (np.histogram: searchsorted semantics, last
+ * bin closed), optional division by the normalised per-bin exposure of the GTIs
+ * (stingray.pulse.pulsar.phase_exposure), then chi^2 (nharm == 0) or binned Z^2_nharm.
+ *
+ *   times    [n_ev]   event times (or light-curve bin times) of ONE segment, as upstream passes them
+ *   weights  [n_ev]   or NULL: every event weighs `unit_weight`
+ *   gti      [n_gti*2] HOST array of (start, stop) pairs in the frame of `times`; n_gti == 0: no exposure
+ *            correction.  start_time / stop_time: times[0] and times[-1] + |times[1] - times[0]|
+ *   stats    [n_fd * n_f]; profiles [n_fd * n_f * nbin] fp64 (exposure-corrected) or NULL
+ */
+int hx_wfold_search(const double *times, const double *weights, double unit_weight, int64_t n_ev, const double *freqs,
+                    int64_t n_f, const double *fdots, int64_t n_fd, int nbin, int nharm, const double *gti,
+                    int64_t n_gti, double start_time, double stop_time, double *stats, double *profiles, int device);
+int hx_wfold_search_dev(const double *d_times, const double *d_weights, double unit_weight, int64_t n_ev,
+                        const double *d_freqs, int64_t n_f, const double *d_fdots, int64_t n_fd, int nbin, int nharm,
+                        const double *gti, int64_t n_gti, double start_time, double stop_time, double *d_stats,
+                        double *d_profiles, void *stream);
+/* Device time of the wfold_kernel launches of the most recent hx_wfold_search* call. */
+int hx_wfold_last_kernel_ms(double *ms);
+
 /* ---- K2 + K3: one centre step of the `--fast` quasi-fast-folding search ------------------
  * Replaces hendrics/efsearch.py:876-925 (search_with_qffa_step) = _fast_phase* (:854-873) +
  * histogram2d (hendrics/base.py:667-693) + _fast_step (:817-851) for `n_centres` centre

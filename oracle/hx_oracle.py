@@ -364,17 +364,174 @@ def folding_search_core(
     return out
 
 
+# --------------------------------------------------------------------------------------
+# The SLOW branch of upstream's searches: stingray.pulse.pulsar.pulse_phase / phase_exposure /
+# fold_events, reached when ``expocorr`` is set or ``weights`` is an array (light-curve input:
+# hendrics/efsearch.py:1155-1157, 1164-1167).
+# [UPSTREAM-RECALLED] -- restated from the published stingray 2.x sources, not checkable here.
+# --------------------------------------------------------------------------------------
+def pulse_phase(times, *frequency_derivatives, ph0=0, to_1=True):
+    """stingray.pulse.pulsar.pulse_phase: ph = ph0 + sum_i times**(i+1) * f_i / (i+1)!."""
+    ph = ph0
+    for i_f, f in enumerate(frequency_derivatives):
+        ph = ph + 1 / math.factorial(i_f + 1) * times ** (i_f + 1) * f
+    if to_1:
+        ph = ph - np.floor(ph)
+    return ph
+
+
+def phase_exposure(start_time, stop_time, period, nbin=16, gti=None):
+    """stingray.pulse.pulsar.phase_exposure: relative exposure of each phase bin, long-double
+    arithmetic on fp64 inputs, accumulated into an fp64 array."""
+    if gti is None:
+        gti = np.array([[start_time, stop_time]])
+    start_time = np.longdouble(start_time)
+    stop_time = np.longdouble(stop_time)
+    period = np.longdouble(period)
+    gti = np.array(gti, dtype=np.longdouble)
+
+    expo = np.zeros(nbin)
+    phs = np.linspace(0, 1, nbin + 1)
+    phs = np.array(list(zip(phs[0:-1], phs[1:])))
+
+    good = np.logical_and(gti[:, 0] < stop_time, gti[:, 1] > start_time)
+    gti = gti[good]
+    for g in gti:
+        g0 = g[0]
+        g1 = g[1]
+        if g0 < start_time:
+            g0 = start_time
+        if g1 > stop_time:
+            g1 = stop_time
+        length = g1 - g0
+        nraw = length / period
+        nper = nraw.astype(int)
+        expo += nper / nbin
+        start_phase = np.fmod(g0 / period, 1)
+        end_phase = nraw - nper + start_phase
+        limits = [[start_phase, end_phase]]
+        if end_phase > 1:
+            limits = [[0, end_phase - 1], [start_phase, 1]]
+        for l in limits:
+            l0 = l[0]
+            l1 = l[1]
+            goodbins = np.logical_and(phs[:, 0] <= l1, phs[:, 1] >= l0)
+            idxs = np.arange(len(phs), dtype=int)[goodbins]
+            for i in idxs:
+                start = np.max([phs[i, 0], l0])
+                stop = np.min([phs[i, 1], l1])
+                w = stop - start
+                expo[i] += w
+    return expo / np.max(expo)
+
+
+def fold_events(times, *frequency_derivatives, nbin=16, weights=1, gti=None, ref_time=0, expocorr=False):
+    """stingray.pulse.pulsar.fold_events, ``mode="ef"``: (weighted) phase histogram over the
+    explicit bin edges ``linspace(0, 1, nbin + 1)`` (np.histogram => searchsorted semantics, right
+    edge of the last bin included), optionally divided by the per-bin exposure.
+    Returns (bin centres, profile, profile error)."""
+    times = np.asarray(times, dtype=np.float64)
+    if gti is None:
+        gti = [[times[0], times[-1]]]
+    gti = np.asanyarray(gti)
+    if not isinstance(weights, np.ndarray) and not isinstance(weights, (list, tuple)):
+        weights = weights * np.ones(len(times))
+    weights = np.asarray(weights)
+    gti = gti - ref_time
+    times = times - ref_time
+    dt = np.abs(times[1] - times[0])
+    start_time = times[0]
+    stop_time = times[-1] + dt
+    phases = pulse_phase(times, *frequency_derivatives, to_1=True)
+    gti_phases = pulse_phase(gti, *frequency_derivatives, to_1=False)
+    start_phase, stop_phase = pulse_phase(np.array([start_time, stop_time]), *frequency_derivatives, to_1=False)
+    bins = np.linspace(0, 1, nbin + 1)
+    raw_profile, bins = np.histogram(phases, bins=bins, weights=weights)
+    raw_profile_err = np.sqrt(np.histogram(phases, bins=bins, weights=weights**2)[0])
+    bins = (bins[1:] + bins[:-1]) / 2
+    if expocorr:
+        expo_norm = phase_exposure(start_phase, stop_phase, 1, nbin, gti=gti_phases)
+    else:
+        expo_norm = 1
+    return bins, raw_profile / expo_norm, raw_profile_err / expo_norm
+
+
+def folding_search_slow(
+    times,
+    frequencies,
+    fdots=0,
+    nbin=128,
+    nharm=0,
+    segment_size=np.inf,
+    expocorr=False,
+    gti=None,
+    weights=1,
+    rezero_to_first_event=True,
+    drop_last_event=True,
+    return_profiles=False,
+):
+    """Upstream ``_folding_search(..., use_times=True)``: per trial ``fold_events`` on the segment's
+    times (array-valued keyword arguments as long as ``times`` are masked like them; the GTIs are
+    passed through UNSHIFTED, as upstream does) followed by ``ef_profile_stat`` (nharm == 0) or
+    ``z_n_binned_events``."""
+    frequencies = np.atleast_1d(np.asarray(frequencies, dtype=np.float64))
+    fdots = np.atleast_1d(np.asarray(fdots, dtype=np.float64))
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    stats = np.zeros_like(fgrid)
+    profiles = np.zeros(fgrid.shape + (nbin,)) if return_profiles else None
+    n_all = len(times)
+    times, masks = select_segments(times, segment_size, rezero_to_first_event, drop_last_event)
+    count = 0
+    for good in masks:
+        ts = times[good]
+        w = weights
+        if isinstance(weights, (np.ndarray, list, tuple)) and len(weights) == n_all:
+            w = np.asarray(weights)[good]
+        g = gti
+        if gti is not None and len(gti) == n_all:  # upstream masks ANY keyword of that length
+            g = np.asarray(gti)[good]
+        for i in range(fgrid.shape[0]):
+            for j in range(fgrid.shape[1]):
+                prof = fold_events(ts, fgrid[i, j], fdgrid[i, j], nbin=nbin, weights=w, gti=g, expocorr=expocorr)[1]
+                if nharm == 0:
+                    stats[i, j] += ef_profile_stat(prof)
+                else:
+                    stats[i, j] += z_n_binned_events(prof, nharm)
+                if return_profiles:
+                    profiles[i, j] += prof
+        count += 1
+    if count > 0:
+        stats = stats / count
+    if fgrid.shape[0] == 1:
+        out = (fgrid.flatten(), stats.flatten())
+    else:
+        out = (fgrid, fdgrid, stats)
+    if return_profiles:
+        out = out + (profiles,)
+    return out
+
+
+def _slow_branch(expocorr, weights):
+    return bool(expocorr) or isinstance(weights, (np.ndarray, list, tuple))
+
+
 def epoch_folding_search(times, frequencies, nbin=128, segment_size=np.inf, expocorr=False, gti=None, weights=1, fdots=0, **kw):
-    """stingray.pulse.search.epoch_folding_search (fast branch only)."""
+    """stingray.pulse.search.epoch_folding_search."""
     if expocorr and gti is None:
         raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    if _slow_branch(expocorr, weights):
+        return folding_search_slow(times, frequencies, fdots=fdots, nbin=nbin, nharm=0, segment_size=segment_size,
+                                   expocorr=expocorr, gti=gti, weights=weights, **kw)
     return folding_search_core(times, frequencies, fdots=fdots, nbin=nbin, nharm=0, segment_size=segment_size, **kw)
 
 
 def z_n_search(times, frequencies, nharm=4, nbin=128, segment_size=np.inf, expocorr=False, weights=1, gti=None, fdots=0, **kw):
-    """stingray.pulse.search.z_n_search (fast, binned branch only)."""
+    """stingray.pulse.search.z_n_search (binned)."""
     if expocorr and gti is None:
         raise ValueError("To calculate exposure correction, you need to specify the GTIs")
+    if _slow_branch(expocorr, weights):
+        return folding_search_slow(times, frequencies, fdots=fdots, nbin=nbin, nharm=nharm, segment_size=segment_size,
+                                   expocorr=expocorr, gti=gti, weights=weights, **kw)
     return folding_search_core(times, frequencies, fdots=fdots, nbin=nbin, nharm=nharm, segment_size=segment_size, **kw)
 
 

@@ -98,3 +98,41 @@ def test_topk_flat_is_deterministic():
     x = np.array([1.0, 5.0, 5.0, 2.0, 5.0])
     idx, val = O.topk_flat(x, 3)
     assert list(idx) == [1, 2, 4] and list(val) == [5.0, 5.0, 5.0]
+
+
+# ---- slow (`fold_events`) branch: weights / exposure correction --------------------------------------
+def test_phase_exposure_known_answers():
+    # an integer number of periods exposes every bin equally
+    np.testing.assert_allclose(O.phase_exposure(0.0, 7.0, 1, 8), np.ones(8), rtol=1e-15)
+    # 2.5 periods from phase 0: the first half of the profile is seen 3 times, the second half twice
+    e = O.phase_exposure(0.0, 2.5, 1, 4)
+    np.testing.assert_allclose(e, [1, 1, 2 / 3, 2 / 3], rtol=1e-15)
+    # a gap: [0, 1.25] + [1.75, 3]: bins 0 and 3 seen 3 times, bins 1 and 2 twice
+    e = O.phase_exposure(0.0, 3.0, 1, 4, gti=np.array([[0.0, 1.25], [1.75, 3.0]]))
+    np.testing.assert_allclose(e, [1, 2 / 3, 2 / 3, 1], rtol=1e-15)
+
+
+def test_fold_events_unit_weights_equals_fast_profile():
+    ts = O.simulate_events(5000, 100.0, seed=8)
+    prof = np.zeros(32, dtype=np.int64)
+    for f, fd in ((9.9, 0.0), (9.91, 1e-5), (3.3, -2e-5)):
+        O._fold_one(ts, f, fd, 32, prof)
+        bins, p, perr = O.fold_events(ts, f, fd, nbin=32)
+        assert np.array_equal(p, prof)
+        np.testing.assert_allclose(bins, (np.arange(32) + 0.5) / 32)
+        np.testing.assert_allclose(perr, np.sqrt(prof))
+        w = np.full(ts.size, 2.0)
+        assert np.array_equal(O.fold_events(ts, f, fd, nbin=32, weights=w)[1], 2 * prof)
+
+
+def test_slow_branch_reduces_to_fast_branch():
+    ts = O.simulate_events(4000, 80.0, seed=4)
+    f = np.arange(9.85, 9.95, 0.01)
+    a = O.z_n_search(ts, f, nharm=2, nbin=64, fdots=[0, 1e-5])
+    b = O.z_n_search(ts, f, nharm=2, nbin=64, fdots=[0, 1e-5], weights=np.ones(ts.size))
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-13)
+    a = O.epoch_folding_search(ts, f, nbin=16, segment_size=30.0)
+    b = O.epoch_folding_search(ts, f, nbin=16, segment_size=30.0, weights=np.ones(ts.size))
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-13)
+    with pytest.raises(ValueError, match="specify the GTIs"):
+        O.epoch_folding_search(ts, f, expocorr=True)
