@@ -58,6 +58,9 @@ struct DeviceInfo {
 };
 // Cached per device; probes dyn_smem_base with a tiny kernel on first use.
 int get_device_info(int device, DeviceInfo *out);
+// [tmin,tmax, fmin,fmax, fdmin,fdmax] of device arrays (hx_fold.cu); HX_ERR_ARG when not finite; synchronizes
+int device_ranges(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f, const double *d_fdots,
+                  int64_t n_fd, double out[6], cudaStream_t st);
 
 // stream-ordered temporary, released on scope exit
 struct AsyncBuf {

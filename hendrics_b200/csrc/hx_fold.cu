@@ -570,6 +570,39 @@ static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
 static int g_fold_pack_override = -1;  // -1 auto, 0 never, 1 whenever possible
 
+// min/max of the event times, trial frequencies and fdots (device arrays): out = [tmin,tmax, fmin,fmax, fdmin,fdmax];
+// fails with HX_ERR_ARG when any of them is not finite.  Synchronizes `st`.
+int device_ranges(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f, const double *d_fdots,
+                  int64_t n_fd, double out[6], cudaStream_t st) {
+    AsyncBuf rng(st);
+    HX_CUDA_TRY(rng.alloc(6 * sizeof(long long)));
+    long long init[6];
+    for (int i = 0; i < 3; i++) init[2 * i] = INT64_MAX, init[2 * i + 1] = INT64_MIN;
+    HX_CUDA_TRY(cudaMemcpyAsync(rng.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (n_ev > 0) {
+        minmax_kernel<<<(int)std::min<long long>((n_ev + 255) / 256, 1184), 256, 0, st>>>(d_times, n_ev,
+                                                                                          rng.as<double>());
+        HX_CHECK_LAUNCH("minmax_kernel");
+    }
+    minmax_kernel<<<(int)std::min<long long>((n_f + 255) / 256, 1184), 256, 0, st>>>(d_freqs, n_f,
+                                                                                     rng.as<double>() + 2);
+    HX_CHECK_LAUNCH("minmax_kernel");
+    minmax_kernel<<<1, 256, 0, st>>>(d_fdots, n_fd, rng.as<double>() + 4);
+    HX_CHECK_LAUNCH("minmax_kernel");
+    long long henc[6];
+    HX_CUDA_TRY(cudaMemcpyAsync(henc, rng.p, sizeof(henc), cudaMemcpyDeviceToHost, st));
+    HX_CUDA_TRY(cudaStreamSynchronize(st));
+    out[0] = out[1] = 0.0;
+    if (n_ev > 0) out[0] = dec_ordered(henc[0]), out[1] = dec_ordered(henc[1]);
+    for (int i = 2; i < 6; i++) out[i] = dec_ordered(henc[i]);
+    for (int i = 0; i < 6; i++)
+        if (!std::isfinite(out[i])) {
+            set_error("hx_fold_search: non-finite times / frequencies / fdots");
+            return HX_ERR_ARG;
+        }
+    return HX_OK;
+}
+
 int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
                          const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
                          uint32_t *d_profiles, cudaStream_t st) {
@@ -595,35 +628,13 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     if (rc) return rc;
 
     // ranges: [tmin,tmax, fmin,fmax, fdmin,fdmax]
+    double r6[6];
+    if ((rc = device_ranges(d_times, n_ev, d_freqs, n_f, d_fdots, n_fd, r6, st)) != HX_OK) return rc;
+    const double tmin = r6[0], tmax = r6[1], fmin = r6[2], fmax = r6[3], fdmin = r6[4], fdmax = r6[5];
     AsyncBuf rng(st);
-    HX_CUDA_TRY(rng.alloc(6 * sizeof(long long) + sizeof(int)));
-    long long init[7];
-    for (int i = 0; i < 3; i++) init[2 * i] = INT64_MAX, init[2 * i + 1] = INT64_MIN;
-    init[6] = 0;
-    HX_CUDA_TRY(cudaMemcpyAsync(rng.p, init, sizeof(init) - 4, cudaMemcpyHostToDevice, st));
-    int *d_err = reinterpret_cast<int *>(rng.as<long long>() + 6);
-    if (n_ev > 0) {
-        minmax_kernel<<<(int)std::min<long long>((n_ev + 255) / 256, 1184), 256, 0, st>>>(d_times, n_ev,
-                                                                                          rng.as<double>());
-        HX_CHECK_LAUNCH("minmax_kernel");
-    }
-    minmax_kernel<<<(int)std::min<long long>((n_f + 255) / 256, 1184), 256, 0, st>>>(d_freqs, n_f,
-                                                                                     rng.as<double>() + 2);
-    HX_CHECK_LAUNCH("minmax_kernel");
-    minmax_kernel<<<1, 256, 0, st>>>(d_fdots, n_fd, rng.as<double>() + 4);
-    HX_CHECK_LAUNCH("minmax_kernel");
-    long long henc[6];
-    HX_CUDA_TRY(cudaMemcpyAsync(henc, rng.p, sizeof(henc), cudaMemcpyDeviceToHost, st));
-    HX_CUDA_TRY(cudaStreamSynchronize(st));
-    double tmin = 0, tmax = 0;
-    if (n_ev > 0) tmin = dec_ordered(henc[0]), tmax = dec_ordered(henc[1]);
-    const double fmin = dec_ordered(henc[2]), fmax = dec_ordered(henc[3]);
-    const double fdmin = dec_ordered(henc[4]), fdmax = dec_ordered(henc[5]);
-    if (!(std::isfinite(tmin) && std::isfinite(tmax) && std::isfinite(fmin) && std::isfinite(fmax) &&
-          std::isfinite(fdmin) && std::isfinite(fdmax))) {
-        set_error("hx_fold_search: non-finite times / frequencies / fdots");
-        return HX_ERR_ARG;
-    }
+    HX_CUDA_TRY(rng.alloc(sizeof(int)));
+    HX_CUDA_TRY(cudaMemsetAsync(rng.p, 0, sizeof(int), st));
+    int *d_err = rng.as<int>();
     const bool has_fd = !(fdmin == 0.0 && fdmax == 0.0);
     const double tabs_ = std::max(std::fabs(tmin), std::fabs(tmax));
     const double fabs_ = std::max(std::fabs(fmin), std::fabs(fmax));

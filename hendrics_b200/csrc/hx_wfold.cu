@@ -10,21 +10,28 @@
 //         profile /= phase_exposure(start_phase, stop_phase, 1, nbin, gti=pulse_phase(gti, f, fd, to_1=False))
 //     -> ef_profile_stat(profile) | z_n_binned_events(profile, nharm)
 //
-// Design: K1's layout with fp64 cells.  lane = trial; every thread owns R trials and, for each, a PRIVATE
-// nbin-bin fp64 histogram column in shared memory laid out [bin][lane] (byte address = bin*256 + lane*8): a
-// warp-wide 64-bit access touches 32 distinct 8-byte slots = 2 conflict-free wavefronts, and because a
-// column belongs to one thread the update is a plain LDS.64 + DADD + STS.64 -- no atomics.  Event times and
-// weights stream through a 2-stage cp.async.bulk (TMA engine) + mbarrier pipeline and are broadcast to all
-// threads.  Bin index: searchsorted semantics of np.histogram on the explicit edges; for power-of-two nbin
-// the edges j/nbin are exact and the bin is floor(phase*nbin) (phase == 1.0 -> last bin, whose right edge is
-// closed); otherwise floor(phase*nbin) is corrected against the edge table (fl(j*fl(1/nbin)), as
-// np.linspace computes it).  Partial profiles always go to a global fp64 scratch [trial/32][bin][32]
-// (RED.ADD.F64, coalesced); wfold_expo_kernel divides it by the per-trial exposure (double-double
-// arithmetic standing in for upstream's long double), wfold_stat_kernel reduces it to chi^2 / Z^2_n.
+// Design: K1's layout (hx_fold.cu).  lane = trial; every thread owns R trials and, for each, a PRIVATE
+// nbin-bin histogram column in shared memory laid out [bin][lane], so a warp-wide access never has a bank
+// conflict and no other thread ever touches the column.  Two cell types:
+//   * CELL_U32 / CELL_UNIT -- the weights are non-negative integers (light-curve counts; checked on the device,
+//     sum < 2^32) or every event weighs the same: 4-byte cells, the update is one fire-and-forget
+//     `red.shared.add.u32 [cell], w` (1 shared-memory wavefront per warp), exact;
+//   * CELL_F64 -- arbitrary fp64 weights: 8-byte cells (2 wavefronts per access), the update is a plain
+//     LDS.64 + DADD + STS.64 (the hardware has no fp64 shared atomic: atomicAdd compiles to a CAS loop).  Events
+//     are processed in register groups of U: all U*R bin addresses first (independent FP64 chains), then per
+//     trial U cell loads in flight; values are forwarded in registers when two events of a group hit the same
+//     cell, so the result is exactly the sequential sum in event order.
+// Event times and weights stream through a 2-stage cp.async.bulk (TMA engine) + mbarrier pipeline and are
+// broadcast to all threads.  Bin index: searchsorted semantics of np.histogram on the explicit edges; for
+// power-of-two nbin the edges j/nbin are exact and the bin is floor(phase*nbin) (phase == 1.0 -> last bin, whose
+// right edge is closed); otherwise floor(phase*nbin) is corrected by at most one against the edges
+// fl(j*fl(1/nbin)) (np.linspace's arithmetic, recomputed in registers).  Partial profiles always go to a global
+// fp64 scratch [trial/32][bin][32] (RED.ADD.F64, coalesced); wfold_expo_kernel divides it by the per-trial
+// exposure (double-double arithmetic standing in for upstream's long double), wfold_stat_kernel reduces it to
+// chi^2 / Z^2_n.
 //
-// Accumulation order differs from np.histogram's (block-wise sort + cumsum + diff), so weighted profiles
-// agree to fp64 rounding (exactly, when the weights are integers -- light-curve counts -- and the sums
-// stay below 2^53); statistics within the 1e-9 tolerance.
+// np.histogram sums weights by block-wise sort + cumsum + diff, so fp64-weighted profiles agree to rounding
+// (exactly when the weights are integers and the sums stay below 2^53); statistics within the 1e-9 tolerance.
 #include <algorithm>
 #include <cstdlib>
 
@@ -32,12 +39,16 @@
 
 namespace hx {
 
-constexpr int WTILE_EV = 1024;       // events per pipeline stage
+constexpr int WTILE_EV = 512;        // events per pipeline stage
+constexpr int WTILE_PAD = 8;         // events of slack behind a stage (the last register group reads past cnt)
 constexpr uint32_t WSMEM_HDR = 16;   // two mbarriers
+
+enum { CELL_F64 = 0, CELL_U32 = 1, CELL_UNIT = 2 };
+enum { WMODE_EDGES = 0, WMODE_FLOOR = 1, WMODE_FAST = 2 };
 
 struct WFoldArgs {
     const double *ev;
-    const double *wt;  // null: unit weights
+    const void *wt;  // CELL_F64: double[n_ev]; CELL_U32: uint32[n_ev]; CELL_UNIT: unused
     long long n_ev;
     const double *freqs;
     long long n_f;
@@ -47,9 +58,8 @@ struct WFoldArgs {
     int warps;
     long long tb0;  // first 32*R-trial block of this launch
     long long ev_per_split;
-    double *scratch;      // [n_tb*R][nbin][32]
-    const double *edges;  // [nbin + 1]
-    double unit_weight;   // weight of every event when wt == null
+    double *scratch;     // [n_tb*R][nbin][32]
+    double unit_weight;  // CELL_UNIT: weight of every event
 };
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -61,42 +71,56 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
 }
 
-// upstream pulse_phase(..., to_1=True) followed by np.histogram's bin search
-template <bool HAS_FD, bool POW2>
-__device__ __forceinline__ int wbin(double t, double tt, double f, double fdh, int nbin, const double *edges) {
+// Byte offset of the bin inside a [bin][lane] column of (1 << SHIFT)/32-byte cells (bin << SHIFT).
+//   WMODE_EDGES  any nbin: upstream pulse_phase(..., to_1=True), then np.histogram's bin search on the edges
+//   WMODE_FLOOR  power-of-two nbin: the edges j/nbin are exact, the bin is floor(phase*nbin), phase == 1.0 -> last
+//   WMODE_FAST   power-of-two nbin and provably non-negative phases: f and 0.5*fd arrive pre-scaled by
+//                nbin << SHIFT (exact), floor() is one round-down add of 1.5*2^52 and the offset is one AND of the
+//                low mantissa word -- the same argument as K1's MODE_POW2 (hx_fold.cu)
+template <bool HAS_FD, int MODE, int SHIFT>
+__device__ __forceinline__ uint32_t wbin_off(double t, double tt, double f, double fdh, int nbin, uint32_t mask,
+                                             double step) {
     double x = __dmul_rn(t, f);
     if (HAS_FD) x = __dadd_rn(x, __dmul_rn(tt, fdh));  // fl(fl(0.5*fl(t*t))*fd) == fl(fl(t*t)*(0.5*fd))
+    if (MODE == WMODE_FAST) return (uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC)) & mask;
     const double fl = __dsub_rn(__dadd_rd(x, HX_MAGIC), HX_MAGIC);
     const double fr = __dsub_rn(x, fl);  // in [0, 1]
-    int b = __double2loint(__dadd_rd(__dmul_rn(fr, (double)nbin), HX_MAGIC));
-    b = min(b, nbin - 1);
-    if (!POW2) {
-        while (b > 0 && fr < edges[b]) b--;
-        while (b < nbin - 1 && fr >= edges[b + 1]) b++;
+    const double y = __dadd_rd(__dmul_rn(fr, (double)nbin), HX_MAGIC);
+    int b = min(__double2loint(y), nbin - 1);
+    if (MODE == WMODE_EDGES) {
+        // np.linspace(0, 1, nbin + 1)[j] = fl(j * step) for j < nbin, exactly 1.0 for j == nbin.  fl(fr * nbin) is
+        // within one ulp of the real product and the edges within one ulp of j / nbin, so the floor is off by at
+        // most one bin.
+        const double bf = (double)b;
+        const double lo = __dmul_rn(bf, step);
+        const double hi = (b + 1 == nbin) ? 2.0 : __dmul_rn(__dadd_rn(bf, 1.0), step);
+        b += (fr >= hi) - (fr < lo);
     }
-    return b;
+    return (uint32_t)b << SHIFT;
 }
 
-template <int R, bool HAS_FD, bool POW2, bool HAS_W>
+template <int R, int U, bool HAS_FD, int MODE, int CELL>
 __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
+    constexpr bool F64 = CELL == CELL_F64;
+    constexpr int SHIFT = F64 ? 8 : 7;                        // log2 of the bytes of one [lane] row
+    constexpr uint32_t WBYTES = F64 ? 8u : CELL == CELL_U32 ? 4u : 0u;  // bytes per event in the weight stage
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbin = a.nbin;
-    const uint32_t blk = (uint32_t)nbin * 256u;  // bytes of one (warp, r) histogram block
-    const uint32_t edges_off = WSMEM_HDR;
-    const uint32_t edges_bytes = ((uint32_t)(nbin + 1) * 8u + 15u) & ~15u;
-    const uint32_t tile_off = edges_off + edges_bytes;
-    constexpr uint32_t TILE_BYTES = WTILE_EV * 8u;
-    const uint32_t hist_off = tile_off + (HAS_W ? 4u : 2u) * TILE_BYTES;
+    const uint32_t blk = (uint32_t)nbin << SHIFT;  // bytes of one (warp, r) histogram block
+    constexpr uint32_t TILE_T = (WTILE_EV + WTILE_PAD) * 8u, TILE_W = (WTILE_EV + WTILE_PAD) * WBYTES;
+    const uint32_t tile_off = WSMEM_HDR, wt_off = tile_off + 2u * TILE_T;
+    const uint32_t hist_off = wt_off + 2u * TILE_W;
     const uint32_t hist = sbase + hist_off;
-    double *s_edges = reinterpret_cast<double *>(smem + edges_off);
 
-    for (uint32_t o = tid * 8; o < (uint32_t)a.warps * R * blk; o += blockDim.x * 8) sts_f64(hist + o, 0.0);
-    for (int i = tid; i <= nbin; i += blockDim.x) s_edges[i] = a.edges[i];
+    for (uint32_t o = tid * 4; o < (uint32_t)a.warps * R * blk; o += blockDim.x * 4) sts_u32(hist + o, 0u);
 
     const long long tbl = (long long)blockIdx.x * a.warps + warp;
     const long long tb = a.tb0 + tbl;
+    const double scale = MODE == WMODE_FAST ? (double)(nbin << SHIFT) : 1.0;
+    const uint32_t mask = (uint32_t)(nbin - 1) << SHIFT;
+    const double step = 1.0 / (double)nbin;
     double f[R], fdh[R];
     uint32_t cb[R];
 #pragma unroll
@@ -105,9 +129,9 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
         const bool valid = g < a.n_trials;
         const long long gi = valid ? g : 0;
         const long long ifd = gi / a.n_f, jf = gi - ifd * a.n_f;
-        f[r] = a.freqs[jf];
-        fdh[r] = HAS_FD ? __dmul_rn(0.5, a.fdots[ifd]) : 0.0;
-        cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * 8u;
+        f[r] = __dmul_rn(a.freqs[jf], scale);
+        fdh[r] = HAS_FD ? __dmul_rn(__dmul_rn(0.5, a.fdots[ifd]), scale) : 0.0;
+        cb[r] = hist + (uint32_t)(warp * R + r) * blk + (uint32_t)lane * (F64 ? 8u : 4u);
     }
 
     const long long e0 = (long long)blockIdx.y * a.ev_per_split;
@@ -115,26 +139,25 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
     const int ntiles = (e1 > e0) ? (int)((e1 - e0 + WTILE_EV - 1) / WTILE_EV) : 0;
     const uint32_t bar[2] = {sbase, sbase + 8};
 
-    // stage `it & 1`: times at tile_off + buf*TILE_BYTES, weights two stages further
+    // one stream (times or weights) of stage `it & 1`: bulk copy of the 16-byte multiple, plain copy of the rest
+    auto issue_one = [&](const char *src, uint32_t dst_off, uint32_t bytes, uint32_t b) -> uint32_t {
+        const uint32_t bulk = bytes & ~15u;
+        for (uint32_t o = bulk; o < bytes; o += 4)  // ordered before the arrive of this thread below
+            *reinterpret_cast<uint32_t *>(smem + dst_off + o) = *reinterpret_cast<const uint32_t *>(src + o);
+        if (bulk) bulk_g2s(sbase + dst_off, src, bulk, b);
+        return bulk;
+    };
     auto issue = [&](int it) {
         const long long s = e0 + (long long)it * WTILE_EV;
-        const int cnt = (int)min((long long)WTILE_EV, e1 - s);
-        const uint32_t bytes = (uint32_t)cnt * 8u, bulk = bytes & ~15u;
-        const uint32_t off_t = tile_off + (uint32_t)(it & 1) * TILE_BYTES;
-        const uint32_t off_w = off_t + 2u * TILE_BYTES;
-        const char *src_t = reinterpret_cast<const char *>(a.ev) + s * 8;
-        const char *src_w = reinterpret_cast<const char *>(a.wt) + s * 8;
-        if (bytes != bulk) {  // odd trailing fp64: plain copy, ordered before the arrive below
-            *reinterpret_cast<double *>(smem + off_t + bulk) = *reinterpret_cast<const double *>(src_t + bulk);
-            if (HAS_W) *reinterpret_cast<double *>(smem + off_w + bulk) = *reinterpret_cast<const double *>(src_w + bulk);
-        }
-        if (bulk) {
-            mbar_expect_tx(bar[it & 1], HAS_W ? 2u * bulk : bulk);
-            bulk_g2s(sbase + off_t, src_t, bulk, bar[it & 1]);
-            if (HAS_W) bulk_g2s(sbase + off_w, src_w, bulk, bar[it & 1]);
-        } else {
-            mbar_arrive(bar[it & 1]);
-        }
+        const uint32_t cnt = (uint32_t)min((long long)WTILE_EV, e1 - s);
+        const uint32_t b = bar[it & 1];
+        const uint32_t tx = ((cnt * 8u) & ~15u) + ((cnt * WBYTES) & ~15u);
+        if (tx) mbar_expect_tx(b, tx);
+        issue_one(reinterpret_cast<const char *>(a.ev) + s * 8, tile_off + (uint32_t)(it & 1) * TILE_T, cnt * 8u, b);
+        if (WBYTES)
+            issue_one(reinterpret_cast<const char *>(a.wt) + s * WBYTES, wt_off + (uint32_t)(it & 1) * TILE_W,
+                      cnt * WBYTES, b);
+        if (!tx) mbar_arrive(b);
     };
 
     if (tid == 0) {
@@ -147,23 +170,67 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
     }
     __syncthreads();
 
-    const double w1 = a.unit_weight;
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
         mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
         const int cnt = (int)min((long long)WTILE_EV, e1 - (e0 + (long long)it * WTILE_EV));
-        const double *tp = reinterpret_cast<const double *>(smem + tile_off + (uint32_t)buf * TILE_BYTES);
-        const double *wp = tp + 2 * WTILE_EV;
-#pragma unroll 2
-        for (int e = 0; e < cnt; e++) {
-            const double t = tp[e];
-            const double w = HAS_W ? wp[e] : w1;
-            const double tt = HAS_FD ? __dmul_rn(t, t) : 0.0;
+        const unsigned char *tp = smem + tile_off + (uint32_t)buf * TILE_T;
+        const unsigned char *wp = smem + wt_off + (uint32_t)buf * TILE_W;
+        for (int e = 0; e < cnt; e += U) {
+            double t[U], tt[HAS_FD ? U : 1];
+            double w[F64 ? U : 1];
+            uint32_t wi[F64 ? 1 : U];
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int b = wbin<HAS_FD, POW2>(t, tt, f[r], fdh[r], nbin, s_edges);
-                const uint32_t ad = cb[r] + ((uint32_t)b << 8);
-                sts_f64(ad, __dadd_rn(lds_f64(ad), w));
+            for (int u = 0; u < U; u += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(tp + (size_t)(e + u) * 8);
+                t[u] = v.x, t[u + 1] = v.y;
+                if (F64) {
+                    const double2 q = *reinterpret_cast<const double2 *>(wp + (size_t)(e + u) * 8);
+                    w[u] = q.x, w[u + 1] = q.y;
+                } else if (CELL == CELL_U32) {
+                    const uint2 q = *reinterpret_cast<const uint2 *>(wp + (size_t)(e + u) * 4);
+                    wi[u] = q.x, wi[u + 1] = q.y;
+                } else {
+                    wi[u] = 1u, wi[u + 1] = 1u;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (e + u >= cnt) {  // ragged end of the last stage: adds zero to a valid cell
+                    t[u] = 0.0;
+                    if (F64) w[u] = 0.0;
+                    else wi[u] = 0u;
+                }
+                if (HAS_FD) tt[u] = __dmul_rn(t[u], t[u]);
+            }
+            uint32_t ad[R][U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    ad[r][u] = cb[r] + wbin_off<HAS_FD, MODE, SHIFT>(t[u], HAS_FD ? tt[u] : 0.0, f[r], fdh[r], nbin,
+                                                                     mask, step);
+            if constexpr (!F64) {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+#pragma unroll
+                    for (int r = 0; r < R; r++) red_shared_add_u32(ad[r][u], wi[u]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    double h[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) h[u] = lds_f64(ad[r][u]);
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        // the cell's current value: what a previous event of this group just stored, if any
+#pragma unroll
+                        for (int v = 0; v < u; v++)
+                            if (ad[r][v] == ad[r][u]) h[u] = h[v];
+                        h[u] = __dadd_rn(h[u], w[u]);
+                        sts_f64(ad[r][u], h[u]);
+                    }
+                }
             }
         }
         __syncthreads();  // every warp is done with stage `buf`
@@ -178,10 +245,35 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
     for (int r = 0; r < R; r++) {
         double *dst = a.scratch + ((size_t)(tbl * R + r) * nbin) * 32 + lane;
         for (int j = 0; j < nbin; j++) {
-            const double c = lds_f64(cb[r] + ((uint32_t)j << 8));
+            double c;
+            if (F64) {
+                c = lds_f64(cb[r] + ((uint32_t)j << SHIFT));
+            } else {
+                c = (double)lds_u32(cb[r] + ((uint32_t)j << SHIFT));
+                if (CELL == CELL_UNIT) c = __dmul_rn(c, a.unit_weight);
+            }
             if (c != 0.0) atomicAdd(dst + (size_t)j * 32, c);
         }
     }
+}
+
+// fp64 weights -> uint32 when every one of them is a non-negative integer; flags[0] = 1 otherwise,
+// flags[1..2] = the 64-bit sum of the integer weights (the u32 cells need it below 2^32)
+__global__ void wfold_intweights_kernel(const double *__restrict__ w, long long n, uint32_t *__restrict__ out,
+                                        unsigned long long *flags) {
+    unsigned long long sum = 0;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = w[i];
+        const bool ok = v >= 0.0 && v < 4294967296.0 && v == floor(v);
+        bad |= !ok;
+        const uint32_t u = ok ? (uint32_t)v : 0u;
+        out[i] = u;
+        sum += u;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(flags, 1ull);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(flags + 1, sum);
 }
 
 // ---- exposure correction -------------------------------------------------------------------------
@@ -305,26 +397,37 @@ __global__ void __launch_bounds__(256) wfold_stat_kernel(const double *__restric
 }
 
 typedef void (*wfold_fn_t)(const WFoldArgs);
-template <int R, bool HAS_FD, bool POW2>
-static wfold_fn_t pick_wfold_W(bool has_w) {
-    return has_w ? wfold_kernel<R, HAS_FD, POW2, true> : wfold_kernel<R, HAS_FD, POW2, false>;
+template <int R, int U, int CELL>
+static wfold_fn_t pick_wfold_M(bool has_fd, int mode) {
+    if (has_fd)
+        return mode == WMODE_FAST    ? wfold_kernel<R, U, true, WMODE_FAST, CELL>
+               : mode == WMODE_FLOOR ? wfold_kernel<R, U, true, WMODE_FLOOR, CELL>
+                                     : wfold_kernel<R, U, true, WMODE_EDGES, CELL>;
+    return mode == WMODE_FAST    ? wfold_kernel<R, U, false, WMODE_FAST, CELL>
+           : mode == WMODE_FLOOR ? wfold_kernel<R, U, false, WMODE_FLOOR, CELL>
+                                 : wfold_kernel<R, U, false, WMODE_EDGES, CELL>;
 }
-template <int R>
-static wfold_fn_t pick_wfold_R(bool has_fd, bool pow2, bool has_w) {
-    if (has_fd) return pow2 ? pick_wfold_W<R, true, true>(has_w) : pick_wfold_W<R, true, false>(has_w);
-    return pow2 ? pick_wfold_W<R, false, true>(has_w) : pick_wfold_W<R, false, false>(has_w);
+// fp64 cells: (R, U) in {1, 2} x {2, 4}; u32 cells: (1, 4), (2, 2), (4, 2)
+template <int CELL>
+static wfold_fn_t pick_wfold_u32(int R, bool has_fd, int mode) {
+    return R == 4 ? pick_wfold_M<4, 2, CELL>(has_fd, mode)
+           : R == 2 ? pick_wfold_M<2, 2, CELL>(has_fd, mode)
+                    : pick_wfold_M<1, 4, CELL>(has_fd, mode);
 }
-static wfold_fn_t pick_wfold(int R, bool has_fd, bool pow2, bool has_w) {
-    switch (R) {
-        case 4: return pick_wfold_R<4>(has_fd, pow2, has_w);
-        case 2: return pick_wfold_R<2>(has_fd, pow2, has_w);
-        default: return pick_wfold_R<1>(has_fd, pow2, has_w);
-    }
+static wfold_fn_t pick_wfold(int cell, int R, int U, bool has_fd, int mode) {
+    if (cell == CELL_U32) return pick_wfold_u32<CELL_U32>(R, has_fd, mode);
+    if (cell == CELL_UNIT) return pick_wfold_u32<CELL_UNIT>(R, has_fd, mode);
+    if (R == 2) return U == 2 ? pick_wfold_M<2, 2, CELL_F64>(has_fd, mode) : pick_wfold_M<2, 4, CELL_F64>(has_fd, mode);
+    return U == 2 ? pick_wfold_M<1, 2, CELL_F64>(has_fd, mode) : pick_wfold_M<1, 4, CELL_F64>(has_fd, mode);
 }
+
+static int g_wfold_R = 0, g_wfold_U = 0, g_wfold_W = 0;  // tuning hooks (hx_wfold_set_tuning)
+static int g_wfold_force_generic = 0;                    // bit 0: no WMODE_FAST; bit 1: fp64 cells even for integers
 
 static cudaEvent_t g_wev0[64], g_wev1[64];
 static bool g_wev_ok[64] = {false};
 static int g_wlast_device = -1;
+static int g_wlast_cell = -1;
 
 int wfold_search_dev_impl(const double *d_times, const double *d_weights, double unit_weight, int64_t n_ev,
                           const double *d_freqs, int64_t n_f, const double *d_fdots, int64_t n_fd, int nbin,
@@ -352,30 +455,79 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
     int rc = get_device_info(device, &di);
     if (rc) return rc;
 
+    double r6[6];
+    if ((rc = device_ranges(d_times, n_ev, d_freqs, n_f, d_fdots, n_fd, r6, st)) != HX_OK) return rc;
+    const double tmin = r6[0], tmax = r6[1], fmin = r6[2], fmax = r6[3], fdmin = r6[4], fdmax = r6[5];
     // fdot == 0 everywhere: the fdot term adds +0.0 upstream, skip it
-    std::vector<double> h_fd((size_t)n_fd);
-    HX_CUDA_TRY(cudaMemcpyAsync(h_fd.data(), d_fdots, (size_t)n_fd * 8, cudaMemcpyDeviceToHost, st));
-    HX_CUDA_TRY(cudaStreamSynchronize(st));
-    bool has_fd = false;
-    for (double v : h_fd) has_fd |= (v != 0.0);
-
+    const bool has_fd = !(fdmin == 0.0 && fdmax == 0.0);
+    const double tabs_ = std::max(std::fabs(tmin), std::fabs(tmax));
+    const double phmax = tabs_ * std::max(std::fabs(fmin), std::fabs(fmax)) +
+                         0.5 * tabs_ * tabs_ * std::max(std::fabs(fdmin), std::fabs(fdmax));
+    if (!(phmax < 1125899906842624.0 /* 2^50 */)) {
+        set_error("hx_wfold_search: |phase| up to %.3g cycles exceeds the fp64 folding range (2^50)", phmax);
+        return HX_ERR_RANGE;
+    }
+    // ---- cell type: u32 counters when the weights are integers (or absent), fp64 cells otherwise
+    AsyncBuf b_wi(st), b_flags(st);
+    int cell = d_weights ? CELL_F64 : CELL_UNIT;
+    const void *d_wt = d_weights;
+    if (d_weights && n_ev > 0 && !(g_wfold_force_generic & 2)) {
+        HX_CUDA_TRY(b_wi.alloc((size_t)n_ev * sizeof(uint32_t)));
+        HX_CUDA_TRY(b_flags.alloc(2 * sizeof(unsigned long long)));
+        HX_CUDA_TRY(cudaMemsetAsync(b_flags.p, 0, 2 * sizeof(unsigned long long), st));
+        wfold_intweights_kernel<<<(int)std::min<long long>((n_ev + 255) / 256, 1184), 256, 0, st>>>(
+            d_weights, n_ev, b_wi.as<uint32_t>(), b_flags.as<unsigned long long>());
+        HX_CHECK_LAUNCH("wfold_intweights_kernel");
+        unsigned long long hf[2];
+        HX_CUDA_TRY(cudaMemcpyAsync(hf, b_flags.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
+        HX_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hf[0] == 0 && hf[1] < 4294967296ull) cell = CELL_U32, d_wt = b_wi.p;
+    }
+    const bool f64 = cell == CELL_F64;
+    const int shift = f64 ? 8 : 7;
     const bool pow2 = (nbin & (nbin - 1)) == 0;
-    const bool has_w = d_weights != nullptr;
-    // plan: trials per thread and warps per CTA from the fp64 histogram footprint (256 B per bin and warp)
-    int R = nbin <= 16 ? 4 : nbin <= 64 ? 2 : 1;
-    const uint32_t edges_bytes = ((uint32_t)(nbin + 1) * 8u + 15u) & ~15u;
-    const uint32_t fixed = WSMEM_HDR + edges_bytes + (has_w ? 4u : 2u) * WTILE_EV * 8u;
-    const uint32_t blk = (uint32_t)nbin * 256u;
+    // same conditions as K1's fast path: non-negative phases (ph - floor(ph) is then exact) inside the magic-add range
+    const bool nonneg = tmin >= 0 && fmin >= 0 && (fdmin >= 0 || fmin + 0.5 * tmax * fdmin * (1 + 1e-12) > 0);
+    int mode = !pow2 ? WMODE_EDGES
+               : (nonneg && phmax * (double)(nbin << shift) < 1125899906842624.0) ? WMODE_FAST
+                                                                                  : WMODE_FLOOR;
+    if ((g_wfold_force_generic & 1) && mode == WMODE_FAST) mode = WMODE_FLOOR;
+    // ---- plan.  A column costs (1 << shift) bytes per bin and warp; the fewer warps fit, the more independent
+    // work per thread is needed: R trials, and for fp64 cells register groups of U events (U cell loads in flight).
+    int R, U;
+    if (f64) {
+        R = 2, U = nbin <= 32 ? 2 : 4;
+        if (g_wfold_R == 1 || g_wfold_R == 2) R = g_wfold_R;
+        if (g_wfold_U == 2 || g_wfold_U == 4) U = g_wfold_U;
+    } else {
+        R = nbin <= 32 ? 4 : nbin <= 64 ? 2 : 1;  // measured on B200 (tools/sweep_wfold.py)
+        if (g_wfold_R) R = g_wfold_R;
+        U = R == 1 ? 4 : 2;
+    }
+    const uint32_t wbytes = f64 ? 8u : cell == CELL_U32 ? 4u : 0u;
+    const uint32_t fixed = WSMEM_HDR + 2u * (WTILE_EV + WTILE_PAD) * (8u + wbytes);
+    const uint32_t blk = (uint32_t)nbin << shift;
     int W = 0;
     for (; R >= 1; R >>= 1) {
-        W = std::min<int>(8, (int)(((uint32_t)di.smem_optin - fixed) / ((uint32_t)R * blk)));
+        W = std::min<int>(16, (int)(((uint32_t)di.smem_optin - fixed) / ((uint32_t)R * blk)));
         if (W >= 1) break;
     }
     if (W < 1) {
-        set_error("hx_wfold_search: nbin=%d does not fit in shared memory (fp64 profiles: nbin <= %d)", nbin,
-                  (int)(((uint32_t)di.smem_optin - fixed) / 256u));
+        set_error("hx_wfold_search: nbin=%d does not fit in shared memory (%s cells: nbin <= %d)", nbin,
+                  f64 ? "fp64" : "u32", (int)(((uint32_t)di.smem_optin - fixed) >> shift));
         return HX_ERR_ARG;
     }
+    if (!f64) U = R == 1 ? 4 : 2;
+    {  // k CTAs of W warps per SM: most resident warps, then fewest CTAs
+        int best_warps = 0;
+        for (int k = 1; k <= 8; k++) {
+            const long long room = (long long)di.smem_per_sm / k - (long long)fixed - di.reserved_smem;
+            const int w = (int)std::min<long long>(std::min<long long>(16, room / ((long long)R * blk)),
+                                                   ((long long)di.smem_optin - fixed) / ((long long)R * blk));
+            if (w >= 1 && k * w > best_warps) best_warps = k * w, W = w;
+        }
+    }
+    if (g_wfold_W) W = std::min(W, g_wfold_W);
     const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);
     {  // few trials: smaller CTAs so that every SM gets one
         const long long want = (n_tb + di.sm_count - 1) / di.sm_count;
@@ -426,10 +578,10 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
     }
 
     WFoldArgs a{};
-    a.ev = d_times, a.wt = d_weights, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots;
+    a.ev = d_times, a.wt = d_wt, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots;
     a.n_trials = n_trials, a.nbin = nbin, a.warps = W, a.ev_per_split = ev_per_split;
-    a.scratch = b_scratch.as<double>(), a.edges = b_edges.as<double>(), a.unit_weight = unit_weight;
-    wfold_fn_t fn = pick_wfold(R, has_fd, pow2, has_w);
+    a.scratch = b_scratch.as<double>(), a.unit_weight = unit_weight;
+    wfold_fn_t fn = pick_wfold(cell, R, U, has_fd, mode);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     if (!g_wev_ok[device]) {
         HX_CUDA_TRY(cudaEventCreate(&g_wev0[device]));
@@ -458,7 +610,7 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
             b_scratch.as<double>(), l0, ng, n_trials, nbin, nharm, b_tab.as<double>(), d_stats, d_profiles);
         HX_CHECK_LAUNCH("wfold_stat_kernel");
     }
-    g_wlast_device = device;
+    g_wlast_device = device, g_wlast_cell = cell;
     HX_CUDA_TRY(cudaStreamSynchronize(st));
     return HX_OK;
 }
@@ -467,7 +619,7 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
 
 extern "C" {
 
-int hx_wfold_last_kernel_ms(double *ms) {
+int hx_wfold_last_kernel_ms(double *ms, int *cell_kind) {
     if (!ms || hx::g_wlast_device < 0) {
         hx::set_error("hx_wfold_last_kernel_ms: no weighted fold kernel has been launched");
         return HX_ERR_ARG;
@@ -477,6 +629,15 @@ int hx_wfold_last_kernel_ms(double *ms) {
     HX_CUDA_TRY(cudaEventSynchronize(hx::g_wev1[d]));
     HX_CUDA_TRY(cudaEventElapsedTime(&f, hx::g_wev0[d], hx::g_wev1[d]));
     *ms = f;
+    if (cell_kind) *cell_kind = hx::g_wlast_cell;
+    return HX_OK;
+}
+
+int hx_wfold_set_tuning(int trials_per_thread, int events_per_group, int warps_per_cta, int force_generic) {
+    hx::g_wfold_R = (trials_per_thread == 1 || trials_per_thread == 2 || trials_per_thread == 4) ? trials_per_thread : 0;
+    hx::g_wfold_U = (events_per_group == 2 || events_per_group == 4) ? events_per_group : 0;
+    hx::g_wfold_W = (warps_per_cta >= 1 && warps_per_cta <= 16) ? warps_per_cta : 0;
+    hx::g_wfold_force_generic = force_generic & 3;  // bit 0: never WMODE_FAST; bit 1: fp64 cells even for integers
     return HX_OK;
 }
 

@@ -102,8 +102,9 @@ int hx_wfold_search_dev(const double *d_times, const double *d_weights, double u
                         const double *d_freqs, int64_t n_f, const double *d_fdots, int64_t n_fd, int nbin, int nharm,
                         const double *gti, int64_t n_gti, double start_time, double stop_time, double *d_stats,
                         double *d_profiles, void *stream);
-/* Device time of the wfold_kernel launches of the most recent hx_wfold_search* call. */
-int hx_wfold_last_kernel_ms(double *ms);
+/* Device time of the wfold_kernel launches of the most recent hx_wfold_search* call and the histogram cell type it
+ * chose: 0 = fp64 cells (arbitrary weights), 1 = uint32 cells (integer weights), 2 = uint32 cells (no weight array). */
+int hx_wfold_last_kernel_ms(double *ms, int *cell_kind);
 
 /* ---- K2 + K3: one centre step of the `--fast` quasi-fast-folding search ------------------
  * Replaces hendrics/efsearch.py:876-925 (search_with_qffa_step) = _fast_phase* (:854-873) +
@@ -180,6 +181,8 @@ int hx_qffa_last_kernel_ms(double *ms, int64_t *launches);
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);
+/* force_generic bit 0: never use the pre-scaled fast bin path; bit 1: fp64 cells even for integer weights */
+int hx_wfold_set_tuning(int trials_per_thread, int events_per_group, int warps_per_cta, int force_generic);
 int hx_fold_set_packing(int mode); /* 0: never pack counters, 1: whenever possible, other: automatic */
 
 #ifdef __cplusplus

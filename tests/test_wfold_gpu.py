@@ -217,3 +217,58 @@ def test_cli_from_light_curve_and_expocorr(tmp_path):
                                     expocorr=True, gti=gti - 8e7)
     np.testing.assert_allclose(ef.stat, rs, rtol=RTOL_STAT)
     assert abs(ef.freq[np.argmax(ef.stat)] - PULSE_F) < 1 / 25.25
+
+
+@pytest.mark.parametrize("nbin", [16, 50, 128])
+def test_cell_types_agree(nbin):
+    """integer weights through the u32 cells == the same through the fp64 cells == the oracle; weights whose sum
+    does not fit in 32 bits fall back to the fp64 cells; the pre-scaled bin path == the generic one."""
+    from hendrics_b200 import _cabi
+    from hendrics_b200.search import fold_profiles_weighted
+
+    rng = np.random.default_rng(nbin)
+    ts = O.simulate_events(20011, 150.0, seed=nbin + 1)
+    w = rng.poisson(2.5, ts.size).astype(np.float64)
+    freqs = 9.85 + 0.002 * np.arange(70)
+    fdots = [0.0, 1e-6]
+    ref_p = _oracle_profiles(ts, freqs, fdots, nbin, w)
+    lib = _cabi.lib()
+    try:
+        for force, want_cell in ((0, 1), (1, 1), (2, 0), (3, 0)):
+            lib.hx_wfold_set_tuning(0, 0, 0, force)
+            _, prof = fold_profiles_weighted(ts, freqs, fdots, nbin=nbin, nharm=1, weights=w)
+            assert _cabi.wfold_last_kernel()[1] == want_cell
+            assert np.array_equal(prof, ref_p)
+        lib.hx_wfold_set_tuning(0, 0, 0, 0)
+        big = w.copy()
+        big[:3] = 2.0**31
+        _, prof = fold_profiles_weighted(ts, freqs[:5], [0.0], nbin=nbin, nharm=1, weights=big)
+        assert _cabi.wfold_last_kernel()[1] == 0
+        assert np.array_equal(prof, _oracle_profiles(ts, freqs[:5], [0.0], nbin, big))
+        _, prof = fold_profiles_weighted(ts, freqs[:5], [0.0], nbin=nbin, nharm=1, weights=1)
+        assert _cabi.wfold_last_kernel()[1] == 2
+        for R, U in ((1, 2), (1, 4), (2, 2), (2, 4), (4, 0)):
+            lib.hx_wfold_set_tuning(R, U, 3, 0)
+            _, p1 = fold_profiles_weighted(ts, freqs, fdots, nbin=nbin, nharm=1, weights=w)
+            _, p2 = fold_profiles_weighted(ts, freqs, fdots, nbin=nbin, nharm=1, weights=w + 0.5)
+            assert np.array_equal(p1, ref_p)
+            np.testing.assert_allclose(p2, _oracle_profiles(ts, freqs, fdots, nbin, w + 0.5), rtol=1e-12)
+    finally:
+        lib.hx_wfold_set_tuning(0, 0, 0, 0)
+
+
+def test_negative_phases_take_the_generic_bin_path():
+    """times before the reference epoch (negative phases): ph - floor(ph) rounds, the fast path is not allowed."""
+    from hendrics_b200.search import fold_profiles_weighted
+
+    rng = np.random.default_rng(5)
+    ts = O.simulate_events(9000, 90.0, seed=5) - 45.0
+    w = rng.uniform(0.2, 3.0, ts.size)
+    freqs = 9.85 + 0.003 * np.arange(40)
+    for nbin in (32, 30):
+        stats, prof = fold_profiles_weighted(ts, freqs, [0.0, -2e-5], nbin=nbin, nharm=2, weights=w)
+        ref_p = _oracle_profiles(ts, freqs, [0.0, -2e-5], nbin, w)
+        np.testing.assert_allclose(prof, ref_p, rtol=1e-12)
+        np.testing.assert_allclose(stats, _oracle_stats(ref_p, 2), rtol=RTOL_STAT)
+        _, pi = fold_profiles_weighted(ts, freqs, [0.0, -2e-5], nbin=nbin, nharm=2, weights=np.ones(ts.size))
+        assert np.array_equal(pi, _oracle_profiles(ts, freqs, [0.0, -2e-5], nbin, 1))
