@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the HENDRICS periodicity-search hot path on B200 ("Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c5|w1|w2] [--impl reference]
 
 One "step" = one pass of the search over this rank's slice of the trial grid on a synthetic
 HENfake-style event list.  Default workload = BASELINE.json configs[1] (C2: HENefsearch, epoch
@@ -356,17 +356,225 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+# Weighted / exposure-corrected fold (K1w): light-curve input (weights = counts per bin) and `--expocorr`.
+# name -> (description, n_bins_or_events, T, n_freq per GPU, f_start, f_step, nbin, nharm, weights, n_gti, seed)
+WEIGHTED = {
+    "w1": ("W1: HENzsearch from a light curve (weights = counts per bin), Z^2_2 nbin=64, 2e6 time bins x 1e5 trial frequencies",
+           2_000_000, 1e5, 100_000, 9.4, 5e-6, 64, 2, "counts", 0, 11),
+    "w2": ("W2: HENefsearch --expocorr with fractional weights, nbin=32, 1e6 events x 1e5 trial frequencies, 50 GTIs",
+           1_000_000, 1e5, 100_000, 9.4, 5e-6, 32, 0, "float", 50, 12),
+}
+
+
+def weighted_inputs(wl, rank, world):
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, n_f, f0, fstep, nbin, nharm, wkind, n_gti, seed = WEIGHTED[wl]
+    rng = np.random.default_rng(seed)
+    if wkind == "counts":  # a light curve: photons of a pulsed source binned at dt = T / n_ev
+        ph = simulate_events(6 * n_ev, T, seed=seed)
+        edges = np.linspace(0.0, T, n_ev + 1)
+        weights = np.histogram(ph, bins=edges)[0].astype(np.float64)
+        times = (edges[:-1] + edges[1:]) / 2
+    else:
+        times = simulate_events(n_ev, T, seed=seed)
+        weights = rng.uniform(0.5, 1.5, n_ev)
+    gti = None
+    if n_gti:
+        e = np.linspace(0.0, T, n_gti + 1)
+        gti = np.stack([e[:-1], e[1:] - 0.37 * (e[1] - e[0])], axis=1)
+        keep = np.zeros(times.size, bool)
+        for g0, g1 in gti:
+            keep |= (times >= g0) & (times < g1)
+        times, weights = times[keep], weights[keep]
+    freqs = f0 + fstep * (rank * n_f + np.arange(n_f, dtype=np.float64))
+    return desc, times, weights, gti, freqs, nbin, nharm
+
+
+def weighted_cpu_rate(times, weights, gti, freqs, nbin, nharm, target_s=10.0):
+    """The oracle's restatement of upstream's fold_events branch (numpy, 1 thread -- upstream's trial loop is
+    serial Python) on the first S trial frequencies."""
+    from oracle import hx_oracle as O
+
+    kw = dict(nbin=nbin, weights=weights, expocorr=gti is not None, gti=gti)
+    fn = (lambda f: O.epoch_folding_search(times, f, **kw)) if nharm == 0 else (lambda f: O.z_n_search(times, f, nharm=nharm, **kw))
+    t0 = time.perf_counter()
+    fn(freqs[:2])
+    per = (time.perf_counter() - t0) / 2
+    s = int(max(2, min(freqs.size, target_s / per)))
+    t0 = time.perf_counter()
+    fn(freqs[:s])
+    dt = time.perf_counter() - t0
+    return (times.size - 1) * s / dt, 1, f"oracle numpy restatement of fold_events (np.histogram per trial, 1 thread), {times.size - 1} events x {s} freqs, {dt:.1f} s"
+
+
+def run_weighted_reference(args):
+    wl = args.workload
+    desc, times, weights, gti, freqs, nbin, nharm = weighted_inputs(wl, 0, 1)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, cores, sample = weighted_cpu_rate(times, weights, gti, freqs, nbin, nharm, target_s=8.0)
+        if k >= args.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(times.size)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_weighted(args):
+    """K1w: value/e2e in (weighted) event*trials/s; roofline of wfold_kernel against the FP64 pipe like K1."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hendrics_b200 import _cabi, epoch_folding_search, z_n_search
+    from hendrics_b200.search import wfold_stats_device
+
+    wl = args.workload
+    desc, times, weights, gti, freqs, nbin, nharm = weighted_inputs(wl, rank, world)
+    dev = torch.device("cuda", local_rank)
+    # event selection of the public API (A1/A2) done once for the resident leg
+    sel = (times - times[0]) < (times[-1] - times[0])
+    ts_host, w_host = (times - times[0])[sel], weights[sel]
+    ts_d, w_d = torch.from_numpy(ts_host).to(dev), torch.from_numpy(w_host).to(dev)
+    f_d = torch.from_numpy(freqs).to(dev)
+    fd_d = torch.zeros(1, dtype=torch.float64, device=dev)
+    kw = dict(gti=gti, start_time=ts_host[0], stop_time=ts_host[-1] + abs(ts_host[1] - ts_host[0]))
+    units_local = float(ts_host.size) * freqs.size
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = [torch.empty((1, freqs.size), dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step_resident():
+        stats = wfold_stats_device(ts_d, w_d, 1.0, f_d, fd_d, nbin, nharm, **kw)
+        if world > 1:
+            dist.all_gather(gathered, stats)
+        return stats
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms, t_wall0 = [], time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+        kern_ms.append(_cabi.wfold_last_kernel()[0])
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    cell = _cabi.wfold_last_kernel()[1]
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = units_local * world * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    pin_t, pin_w, pin_f = (torch.from_numpy(x).pin_memory() for x in (times, weights, freqs))
+    t_np, w_np, f_np = pin_t.numpy(), pin_w.numpy(), pin_f.numpy()
+    api_kw = dict(nbin=nbin, weights=w_np, expocorr=gti is not None, gti=gti)
+
+    def step_e2e():
+        res = epoch_folding_search(t_np, f_np, **api_kw) if nharm == 0 else z_n_search(t_np, f_np, nharm=nharm, **api_kw)
+        stats = res[-1]
+        if world > 1:
+            from hendrics_b200 import dist as hdist
+            stats = hdist.all_gather_concat(stats, [freqs.size] * world, axis=-1)
+        return stats
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_local * world * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        k_ms = float(np.mean(kern_ms))
+        peak_ops = _cabi.microbench(1, reps=5, device=local_rank)
+        mix_ceiling = _cabi.microbench(5, reps=3, device=local_rank)
+        achieved = 4.0 * units_local / (k_ms * 1e-3)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", f"wfold_{wl}_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "fp64_pipe", "achieved": achieved * 1e-12, "peak": peak_ops * 1e-12, "unit": "TFLOP/s",
+            "frac": achieved / peak_ops, "traffic": traffic, "kernel": "hx::wfold_kernel",
+            "cells": {0: "fp64 (LDS.64 + DADD + STS.64 on private columns)", 1: "uint32 (red.shared.add.u32, integer weights)",
+                      2: "uint32 (unit increments)"}[cell],
+            "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
+            "algorithmic_fp64_ops_per_event_trial": 4.0,
+            "mix_ceiling_units_per_s": mix_ceiling, "frac_of_mix_ceiling": units_local / (k_ms * 1e-3) / mix_ceiling,
+            "peak_source": "measured in this process: hx_microbench kind 1 (DMUL+DADD issue rate, non-FMA op/s)",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, sample = weighted_cpu_rate(times, weights, gti, freqs, nbin, nharm)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(ts_host.size),
+                       "n_freq_per_gpu": int(freqs.size), "n_gti": 0 if gti is None else int(len(gti)),
+                       "parallelism": f"trial-grid sharding x{world}, events replicated, one all-gather of stats",
+                       "l2": "flushed between timed iterations (256 MiB write)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(times.nbytes + weights.nbytes + freqs.nbytes),
+                    "d2h_bytes_per_step": int(freqs.size * 8)},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"] + sorted(WEIGHTED))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = args.workload
+    if wl in WEIGHTED:
+        return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
     if args.impl == "reference":
         return run_reference(args, wl)
     if wl == "c4":

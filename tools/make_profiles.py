@@ -29,7 +29,8 @@ def num(s):
     return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}.get(u, 1)
 
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
-for w, name in (('c2', 'fold_c2'), ('c3', 'fold_c3'), ('c4', 'qffa_c4')):
+which = sys.argv[2].split(',') if len(sys.argv) > 2 else ['c2', 'c3', 'c4']
+for w, name in [x for x in (('c2', 'fold_c2'), ('c3', 'fold_c3'), ('c4', 'qffa_c4'), ('w1', 'wfold_w1'), ('w2', 'wfold_w2')) if x[0] in which]:
     launch_summary(w, tag)
     subprocess.run([sys.executable, 'tools/ncu_summary.py', f'gpurun_out/bench_{w}_top.ncu-rep', f'profiles/{tag}_ncu_bench_{w}_top.json'], stdout=subprocess.DEVNULL)
     d = json.load(open(f'profiles/{tag}_ncu_bench_{w}_top.json'))
