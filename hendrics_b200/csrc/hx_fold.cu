@@ -41,6 +41,13 @@
 
 namespace hx {
 
+#ifndef HX_FOLD_SKEW_FD
+#define HX_FOLD_SKEW_FD 0  // 1: skewed software pipeline for the (f, fdot) kernels too (measured on B200: no gain, C3 3.21e12 either way)
+#endif
+#ifndef HX_FOLD_SKEW_UE2
+#define HX_FOLD_SKEW_UE2 4  // events per register group of the skewed (f, fdot) loop with 2 trials per thread
+#endif
+
 constexpr int TILE_EV_MAX = 1024;  // events per pipeline stage (runtime: 256..1024, multiple of 64)
 constexpr int TILE_PAD = 16;       // events of slack after each stage (register prefetch may read past cnt)
 constexpr uint32_t SMEM_HDR = 32;  // two mbarriers + two "warps done" counters
@@ -158,9 +165,10 @@ struct EvGroup {
 
 // events per register group: enough independent DMUL->DADD->DADD.RM->LOP3->ATOMS chains per warp
 // (R*UE) to cover the FP64 latency with the few warps the histograms leave room for
-template <int R, bool HAS_FD>
+template <int R, bool HAS_FD, bool SKEW>
 struct GroupSize {
-    static constexpr int value = HAS_FD ? (R >= 8 ? 2 : R >= 4 ? 4 : 8) : (R >= 4 ? 2 : 4);
+    static constexpr int value = HAS_FD ? (SKEW ? (R >= 4 ? 2 : R >= 2 ? HX_FOLD_SKEW_UE2 : 8) : (R >= 8 ? 2 : R >= 4 ? 4 : 8))
+                                        : (R >= 4 ? 2 : 4);
 };
 
 // ROWFD: the R trials of a thread lie in the same fdot row (trial blocks are laid out row by row, rows
@@ -172,7 +180,8 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     constexpr bool PACKED = MODE == MODE_PACKED;
     constexpr bool EXACT = MODE == MODE_EXACT;
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int UE = GroupSize<R, HAS_FD>::value;
+    constexpr bool SKEW = !EXACT && (!HAS_FD || HX_FOLD_SKEW_FD);  // the exact-phase extension keeps the plain loop
+    constexpr int UE = GroupSize<R, HAS_FD, SKEW>::value;
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t blk = (uint32_t)a.nbin << (PACKED ? 6 : 7);  // bytes of one (warp, r) histogram block
@@ -301,41 +310,38 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 
         int e = 0;
         EvGroup<HAS_FD, UE, EXACT> cur, nxt;
-        if constexpr (!HAS_FD) {
+        if constexpr (SKEW) {
         // Skewed software pipeline: the bin addresses of group g+1 are computed (FP64 pipe) while the
         // increments of group g are issued (LSU), so the two instruction classes interleave finely
         // instead of alternating in long runs.
         uint32_t ad_cur[UE * R], inc_cur[PACKED ? UE * R : 1], ad_nxt[UE * R], inc_nxt[PACKED ? UE * R : 1];
-        auto addresses = [&](EvGroup<HAS_FD, UE, EXACT> &g, uint32_t *ad, uint32_t *incs) {
-            g.squares();
-#pragma unroll
-            for (int u = 0; u < UE; u++) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    uint32_t inc;
-                    ad[u * R + r] = bin_addr<HAS_FD, MODE>(g.t[u], 0.0, 0.0, 0.0, fN[r], fdH[r], mask,
-                                                           topbit, nbin, cb[r], inc);
-                    if (PACKED) incs[u * R + r] = inc;
-                }
-            }
+        auto addr1 = [&](const EvGroup<HAS_FD, UE, EXACT> &g, int u, int r, uint32_t &inc) -> uint32_t {
+            const int uu = HAS_FD ? u : 0;
+            const double m2 = ROWFD ? g.m2[uu] : (HAS_FD ? __dmul_rn(g.tt[uu], fdH[r]) : 0.0);
+            return bin_addr<HAS_FD, MODE>(g.t[u], HAS_FD ? g.tt[uu] : 0.0, 0.0, m2, fN[r], fdH[r], mask, topbit, nbin,
+                                          cb[r], inc);
         };
         const int ngroups = cnt / UE;
         if (ngroups > 0) {
             cur.load(tp, 0);
             nxt.load(tp, UE);
-            addresses(cur, ad_cur, inc_cur);
+            cur.squares(fdH_row);
+#pragma unroll
+            for (int i = 0; i < UE * R; i++) {
+                uint32_t inc;
+                ad_cur[i] = addr1(cur, i / R, i % R, inc);
+                if (PACKED) inc_cur[i] = inc;
+            }
             for (int g = 0; g < ngroups; g++) {
                 // group g+1 (garbage past the last group: computed, never issued)
 #pragma unroll
                 for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
                 nxt.load(tp, (g + 2) * UE);  // may read the pad after the stage; never used past cnt
-                cur.squares();
+                cur.squares(fdH_row);
 #pragma unroll
                 for (int i = 0; i < UE * R; i++) {
-                    const int u = i / R, r = i % R;
                     uint32_t inc;
-                    ad_nxt[i] = bin_addr<HAS_FD, MODE>(cur.t[u], 0.0, 0.0, 0.0, fN[r], fdH[r], mask,
-                                                       topbit, nbin, cb[r], inc);
+                    ad_nxt[i] = addr1(cur, i / R, i % R, inc);
                     if (PACKED) inc_nxt[i] = inc;
                     if (PACKED) red_shared_add(ad_cur[i], inc_cur[i]);
                     else red_shared_inc(ad_cur[i]);

@@ -91,11 +91,119 @@ __global__ void __launch_bounds__(256) mb_mix_kernel(uint32_t *out, double a, do
     if (s != (uint32_t)MB_ITERS * MB_ILP) atomicAdd(out, 1u);
 }
 
+// kind 6: F2I.S64.F64.FLOOR issue rate (the XU pipe's fp64 -> int64 conversion)
+__global__ void __launch_bounds__(256) mb_f2i_kernel(double *out, double a) {
+    double x[MB_ILP];
+#pragma unroll
+    for (int i = 0; i < MB_ILP; i++) x[i] = a * (double)(threadIdx.x + i + 1) * 1048576.0;
+    long long acc = 0;
+    for (int it = 0; it < MB_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < MB_ILP; i++) {
+            const long long v = __double2ll_rd(x[i]);
+            acc ^= v;
+            x[i] = __longlong_as_double(__double_as_longlong(x[i]) + (v & 1));  // integer dependency, no FP64/XU op
+        }
+    }
+    if (acc == 0x123456789abcdefLL) out[0] = (double)acc;
+}
+
+// kinds 7..10: the (f, fdot) mix of kind 4 with NF2I of every 8 units taking their floor through F2I.S64.F64.FLOOR
+// (XU pipe) instead of the round-down add of 1.5*2^52 (FP64 pipe): does splitting the floor over two pipes pay?
+template <int NF2I>
+__global__ void __launch_bounds__(256) mb_mix_f2i_kernel(uint32_t *out, double a, double b) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const uint32_t base = smem_u32(dsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cb = base + (uint32_t)warp * 2048u + lane * 4u;
+    for (int j = 0; j < 16; j++) sts_u32(cb + j * 128, 0u);
+    double x[MB_ILP];
+#pragma unroll
+    for (int i = 0; i < MB_ILP; i++) x[i] = a * (double)(threadIdx.x + 3 * i + 1);
+    for (int it = 0; it < MB_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < MB_ILP; i++) {
+            double p = __dmul_rn(x[i], a);
+            p = __dadd_rn(p, __dmul_rn(x[i], b));
+            uint32_t lo;
+            if ((i * NF2I) / 8 != ((i + 1) * NF2I) / 8) {  // NF2I of the 8 chains, evenly spread
+                lo = (uint32_t)__double2ll_rd(p);
+            } else {
+                lo = (uint32_t)__double2loint(__dadd_rd(p, HX_MAGIC));
+            }
+            red_shared_inc((lo & 0x780u) | cb);
+            x[i] = p;
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int j = 0; j < 16; j++) s += lds_u32(cb + j * 128);
+    if (s != (uint32_t)MB_ITERS * MB_ILP) atomicAdd(out, 1u);
+}
+
+// kinds 11/12: K1's (f, fdot) loop at K1's occupancy (4 warps per CTA, ~72 KB of shared memory per CTA => 3 CTAs =
+// 12 warps per SM), 2 trials per thread, events broadcast from a shared-memory tile with LDS.128:
+//   kind 11 (PRE = false): tt = t*t and m2 = tt*fdh computed per event and thread (4 FP64 ops per unit; today's K1)
+//   kind 12 (PRE = true):  m2 read from a second tile, precomputed once per CTA (3 FP64 ops per unit, one more
+//                          shared-memory wavefront per event and warp)
+template <bool PRE>
+__global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a, double b) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const uint32_t base = smem_u32(dsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NEV = 256;
+    double *tile = reinterpret_cast<double *>(dsm);        // [NEV] times
+    double *mtile = tile + NEV;                             // [NEV] fdot terms
+    const uint32_t hist = base + 2 * NEV * 8;
+    uint32_t cb[2];
+    for (int r = 0; r < 2; r++) {
+        cb[r] = hist + (uint32_t)(warp * 2 + r) * 8192u + lane * 4u;  // 64 words x 128 B per column (packed nbin = 128)
+        for (int j = 0; j < 64; j++) sts_u32(cb[r] + j * 128, 0u);
+    }
+    for (int i = threadIdx.x; i < NEV; i += blockDim.x) {
+        tile[i] = 1000.0 + 0.37 * i;
+        mtile[i] = (1000.0 + 0.37 * i) * (1000.0 + 0.37 * i) * b;
+    }
+    __syncthreads();
+    const double f[2] = {a * (1.0 + 1e-6 * (threadIdx.x + 1)) * 16384.0, a * (1.0 + 1e-6 * (threadIdx.x + 129)) * 16384.0};
+    const double fdh = b * 16384.0;
+    for (int it = 0; it < MB_ITERS / 32; it++) {
+#pragma unroll 2
+        for (int e = 0; e < NEV; e += 4) {
+            const double2 t01 = *reinterpret_cast<const double2 *>(tile + e), t23 = *reinterpret_cast<const double2 *>(tile + e + 2);
+            double t[4] = {t01.x, t01.y, t23.x, t23.y}, m[4];
+            if (PRE) {
+                const double2 m01 = *reinterpret_cast<const double2 *>(mtile + e), m23 = *reinterpret_cast<const double2 *>(mtile + e + 2);
+                m[0] = m01.x, m[1] = m01.y, m[2] = m23.x, m[3] = m23.y;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) m[u] = __dmul_rn(__dmul_rn(t[u], t[u]), fdh);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const double y = __dadd_rd(__dadd_rn(__dmul_rn(t[u], f[r]), m[u]), HX_MAGIC);
+                    const uint32_t lo = (uint32_t)__double2loint(y);
+                    red_shared_add_u32((lo & 0x1f80u) | cb[r], (lo & 0x2000u) | 1u);
+                }
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int r = 0; r < 2; r++)
+        for (int j = 0; j < 64; j++) {
+            const uint32_t v = lds_u32(cb[r] + j * 128);
+            s += (v & 0x1fffu);
+        }
+    if (s == 0xffffffffu) atomicAdd(out, 1u);
+}
+
 }  // namespace hx
 
 extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) {
     using namespace hx;
-    if (!ops_per_s || kind < 0 || kind > 5 || reps < 1) {
+    if (!ops_per_s || kind < 0 || kind > 12 || reps < 1) {
         set_error("hx_microbench: bad arguments");
         return HX_ERR_ARG;
     }
@@ -114,6 +222,8 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     const size_t smem = (kind >= 4) ? (size_t)(threads / 32) * 2048 : (kind >= 2) ? (size_t)(threads / 32) * 4 * 2048 : 0;
     if (kind == 2) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (kind == 3) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kind == 11) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 12) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     double best_ms = 1e30;
     for (int r = 0; r < reps + 1; r++) {  // first rep is a warm-up
         HX_CUDA_TRY(cudaEventRecord(e0));
@@ -123,7 +233,14 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
             case 2: mb_smem_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
             case 3: mb_smem_kernel<3><<<grid, threads, smem>>>(out.as<uint32_t>(), (uint32_t)r); break;
             case 4: mb_mix_kernel<4><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
-            default: mb_mix_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 5: mb_mix_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 6: mb_f2i_kernel<<<grid, threads>>>(out.as<double>() + 1, 1.0000001); break;
+            case 7: mb_mix_f2i_kernel<2><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 8: mb_mix_f2i_kernel<4><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 9: mb_mix_f2i_kernel<6><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 10: mb_mix_f2i_kernel<8><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
+            case 11: mb_rowcta_kernel<false><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            default: mb_rowcta_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
         }
         HX_CHECK_LAUNCH("microbench kernel");
         HX_CUDA_TRY(cudaEventRecord(e1));
@@ -136,14 +253,18 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     cudaEventDestroy(e1);
     uint32_t bad = 0;
     HX_CUDA_TRY(cudaMemcpy(&bad, out.p, 4, cudaMemcpyDeviceToHost));
-    if (kind >= 2 && bad) {
+    if (kind >= 2 && kind <= 10 && bad) {
         set_error("hx_microbench: shared-memory counters not conserved (%u warps)", bad);
         return HX_ERR_INTERNAL;
     }
     double per_thread = (kind == 0) ? (double)MB_ITERS * MB_ILP
                       : (kind == 1) ? (double)MB_ITERS * MB_ILP * 2
-                      : (kind >= 4) ? (double)MB_ITERS * MB_ILP  // units (event*trial equivalents)
+                      : (kind >= 4) ? (double)MB_ITERS * MB_ILP  // units (event*trial equivalents; kind 6: F2I)
                                     : (double)MB_ITERS * 4;
+    if (kind >= 11) {
+        *ops_per_s = (double)(MB_ITERS / 32) * 256 * 2 * 128 * (double)(di.sm_count * 6) / (best_ms * 1e-3);
+        return HX_OK;
+    }
     *ops_per_s = per_thread * threads * (double)grid / (best_ms * 1e-3);
     return HX_OK;
 }

@@ -912,9 +912,11 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     // ---- kernel configuration (same footprint classes as K1)
     const bool packed = nbin >= 128;
     const int foot = packed ? nbin / 2 : nbin;
+    // (centres per thread, warps per CTA) measured on B200 (tools/sweep_qlane.py, profiles/r01_sweep_qlane.txt)
     int R = foot <= 32 ? 4 : foot <= 64 ? 2 : 1;
     if (mode >= 1 && R == 4 && foot > 16) R = 2;
-    int W = foot <= 16 ? 8 : 4;
+    int W = foot <= 16 ? 2 : 4;
+    if (packed && foot == 64) R = 1, W = 2;  // nbin = 128 (the --fast default): many small CTAs, 16 resident warps
     // batches of equal size (multiples of 32 centres), bounded by 512 MiB of profile scratch
     const size_t per_centre = (size_t)nprof * nbin * 4;
     const int64_t cap = std::max<int64_t>(32, (int64_t)(((size_t)512 << 20) / per_centre) / 32 * 32);
@@ -926,6 +928,10 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         // CTA columns: as few as possible, each with just enough warps for its share of the slots
         const int gx = (slots_max + R * W - 1) / (R * W);
         W = std::max(1, (slots_max + R * gx - 1) / (R * gx));
+    }
+    if (const char *e = getenv("HX_QLANE_RW")) {  // tuning hook: "R,W"
+        int r = 0, w = 0;
+        if (sscanf(e, "%d,%d", &r, &w) == 2 && (r == 1 || r == 2 || r == 4) && w >= 1 && w <= 16) R = r, W = w;
     }
     const uint32_t blk = (uint32_t)nbin * (packed ? 64u : 128u);
     uint32_t hist_off, tile_off, total;
