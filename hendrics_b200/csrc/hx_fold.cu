@@ -661,7 +661,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     if (fast_ok && nbin <= 256) mode = MODE_POW2;
     // packed counters (two bins per word) for the large profiles, where the plain layout leaves
     // too few resident warps
-    const bool can_pack = fast_ok && nbin >= 128 && nbin <= 512;
+    const bool can_pack = fast_ok && nbin >= 32 && nbin <= 512;
     if (can_pack && (g_fold_pack_override == 1 || (g_fold_pack_override < 0 && nbin >= 128))) mode = MODE_PACKED;
     if (g_fold_pack_override == 0 && mode == MODE_PACKED) mode = nbin <= 256 ? MODE_POW2 : MODE_GENERIC;
     if (flags & HX_FOLD_EXACT_PHASE) mode = MODE_EXACT;
@@ -671,8 +671,8 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     // (tools/sweep_table.py); anything that does not fit falls back to "most resident warps".
     const int foot = mode == MODE_PACKED ? nbin / 2 : nbin;  // histogram words per trial
     int R, W_pref;
-    if (foot <= 16) R = 4, W_pref = has_fd ? 4 : 8;
-    else if (foot <= 32) R = 4, W_pref = has_fd ? 4 : 12;
+    if (foot <= 16) R = has_fd ? 8 : 4, W_pref = has_fd ? 2 : 8;
+    else if (foot <= 32) R = 4, W_pref = 4;
     else if (foot <= 64) R = 2, W_pref = 4;
     else if (foot <= 128) R = 1, W_pref = 12;
     else R = 1, W_pref = 4;
