@@ -141,8 +141,13 @@ def dyn_folding_search(events, fmin, fmax, step=None, func=epoch_folding_search,
     start, stop = time_intervals_from_gtis(gti, time_step)
     stats = []
     frequencies = np.arange(fmin, fmax, step)
+    ev_time = np.asanyarray(events.time)
+    is_sorted = ev_time.size < 2 or bool(np.all(ev_time[1:] >= ev_time[:-1]))
     for st, sp in zip(start, stop):
-        times_filt = events.time[(events.time >= st) & (events.time < sp)]
+        if is_sorted:  # same selection as the mask below, without a pass over the whole list per window
+            times_filt = ev_time[np.searchsorted(ev_time, st, side="left"):np.searchsorted(ev_time, sp, side="left")]
+        else:
+            times_filt = ev_time[(ev_time >= st) & (ev_time < sp)]
         trial_freqs = np.arange(fmin, fmax, step)
         try:
             frequencies, stat = func(times_filt, trial_freqs, **kwargs)
@@ -758,10 +763,16 @@ def _common_main(args, func):
             frequencies, fdots, stats, step, fdotsteps, length = results
 
         if length > args.dynstep and not args.fast:
-            # The reference runs dyn_folding_search here only to draw "Dyn.png" with matplotlib
-            # (efsearch.py:1912-1922) and discards the arrays; without matplotlib the second pass
-            # would be pure waste, so it is skipped.  dyn_folding_search() remains callable.
-            log.info("Skipping the dynamical-search figure (matplotlib-only product)")
+            # efsearch.py:1912-1922: the reference runs the dynamical search here, draws "Dyn.png" with matplotlib
+            # and discards the arrays.  Without matplotlib the arrays the figure is drawn from are saved instead.
+            from . import dist as _dist
+
+            if _dist.rank() == 0:
+                dyn_t, dyn_f, dyn_s = dyn_folding_search(
+                    events, args.fmin, args.fmax, step=step, func=func, oversample=oversample, time_step=args.dynstep,
+                    **kwargs,
+                )
+                np.savez("Dyn.npz", times=dyn_t, frequencies=dyn_f, stats=dyn_s)
 
         efperiodogram = EFPeriodogram(
             frequencies, stats, kind, args.nbin, args.N, fdots=fdots, M=M, segment_size=segment_size, filename=fname,

@@ -166,6 +166,10 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  *   kind 4: the (f, fdot) inner-loop mix (2 DMUL + 2 DADD + LOP3 + ATOMS), no other memory traffic
  *           -> units/s: an empirical ceiling for K1 in event*trials/s
  *   kind 5: the f-only mix (DMUL + DADD + LOP3 + ATOMS) -> units/s
+ *   kind 6: F2I.S64.F64.FLOOR issue rate -> conversions/s
+ *   kinds 7..10: the kind-4 mix with 2, 4, 6, 8 of every 8 floors taken through F2I (XU) instead of the magic add
+ *   kinds 11, 12: K1's (f, fdot) loop at K1's occupancy (12 warps/SM) with the fdot term computed per thread (11) or
+ *           read from a per-CTA shared-memory tile (12) -> units/s   (experiments recorded in DESIGN.md)
  * Runs on `device`, blocks, returns the best of `reps` timings.
  */
 int hx_microbench(int kind, int reps, double *ops_per_s, int device);

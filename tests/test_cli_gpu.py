@@ -112,3 +112,24 @@ def test_dyn_folding_search_and_candidates(evfile):
     rows = _analyze_qffa_results(ef)
     assert 1 <= len(rows) <= 5 and abs(rows[0]["f"] - PULSE_F) < 2 / 25.25
     assert rows[0]["power"] == r[2].max() and rows[0]["f_idx"] == np.unravel_index(np.argmax(r[2]), r[2].shape)[0]
+
+
+def test_cli_runs_the_dynamical_search(evfile, tmp_path, monkeypatch):
+    """efsearch.py:1912-1922: observations longer than --dynstep get the windowed search too; the reference draws
+    Dyn.png from its arrays, here they are saved as Dyn.npz (hendrics/tests/test_efsearch.py:287-316 passes --dynstep 5)."""
+    from hendrics_b200 import z_n_search
+    from hendrics_b200.efsearch import dyn_folding_search, main_zsearch
+    from hendrics_b200.io import load_events
+
+    monkeypatch.chdir(tmp_path)
+    out = main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "-n", "64", "--dynstep", "5"])
+    assert os.path.exists(out[0]) and os.path.exists("Dyn.npz")
+    d = np.load("Dyn.npz")
+    ev = load_events(evfile)
+    step = 1 / 2 / (ev.time[-1] - ev.gti[0, 0])
+    t, f, s = dyn_folding_search(ev, 9.85, 9.95, step=step, func=z_n_search, oversample=2, time_step=5.0, nharm=2)
+    assert d["stats"].shape == (5, f.size) and np.array_equal(d["times"], t) and np.array_equal(d["frequencies"], f)
+    np.testing.assert_allclose(d["stats"], s, rtol=1e-12)
+    # every window is the direct search of its events, from the oracle
+    sel = ev.time[(ev.time >= 8e7 + 5.0) & (ev.time < 8e7 + 10.0)]
+    np.testing.assert_allclose(d["stats"][1], O.z_n_search(sel, f, nharm=2, nbin=128)[1], rtol=1e-9)

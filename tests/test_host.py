@@ -61,7 +61,7 @@ def test_argument_validation_without_gpu():
     assert lib.hx_fold_search(None, 10, _cabi.dptr(t), 1, _cabi.dptr(t), 1, 16, 0, 0, _cabi.dptr(s), None, 0) == _cabi.HX_ERR_ARG
     assert lib.hx_fold_search(_cabi.dptr(t), -1, _cabi.dptr(t), 1, _cabi.dptr(t), 1, 16, 0, 0, _cabi.dptr(s), None, 0) == _cabi.HX_ERR_ARG
     out = ctypes.c_double(0)
-    assert lib.hx_microbench(9, 1, ctypes.byref(out), 0) == _cabi.HX_ERR_ARG
+    assert lib.hx_microbench(99, 1, ctypes.byref(out), 0) == _cabi.HX_ERR_ARG
     assert b"bad arguments" in lib.hx_last_error()
 
 
@@ -181,3 +181,35 @@ def test_sharded_search_gloo_world2(tmp_path):
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("ok") == 2
+
+
+def test_lightcurve_container_and_file_type(tmp_path):
+    """light-curve input of the search path (hendrics/efsearch.py:1154-1157): time / counts / gti round trip."""
+    from hendrics_b200.io import EventList, Lightcurve, get_file_type, save_events, save_lcurve
+
+    t = np.arange(0.5, 100.5)
+    lc = Lightcurve(time=t, counts=np.arange(100), mjdref=55000)
+    assert lc.dt == 1.0 and np.allclose(lc.gti, [[0.0, 100.0]])
+    fn = str(tmp_path / "x_lc.p")
+    save_lcurve(lc, fn)
+    kind, back = get_file_type(fn)
+    assert kind == "lc" and np.array_equal(back.counts, lc.counts) and np.array_equal(back.time, t)
+    assert hasattr(back, "counts") and back.mjdref == 55000
+    fn2 = str(tmp_path / "x_ev.p")
+    save_events(EventList(time=t), fn2)
+    kind, ev = get_file_type(fn2)
+    assert kind == "events" and not hasattr(ev, "counts")
+    with pytest.raises(ValueError):
+        Lightcurve(time=t, counts=np.arange(3))
+
+
+def test_slow_branch_selection_mirrors_upstream():
+    """expocorr or array weights select the fold_events branch; scalar weights do not; expocorr needs the GTIs."""
+    from hendrics_b200 import epoch_folding_search, z_n_search
+    from hendrics_b200.search import _is_slow_branch
+
+    assert _is_slow_branch(True, 1) and _is_slow_branch(False, np.ones(3)) and _is_slow_branch(False, [1, 2])
+    assert not _is_slow_branch(False, 1) and not _is_slow_branch(False, 2.5)
+    for fn in (epoch_folding_search, z_n_search):
+        with pytest.raises(ValueError, match="specify the GTIs"):
+            fn(np.arange(10.0), [1.0], expocorr=True)

@@ -22,6 +22,16 @@ fd = np.arange(-1e-6, 1e-6 + 1e-2 * full[4], full[4])
 ref = z_n_search(t, f, nharm=2, nbin=64, fdots=fd)
 assert np.array_equal(full[0], ref[0]) and np.array_equal(full[1], ref[1])
 assert np.array_equal(full[2], ref[2]), np.abs(full[2] - ref[2]).max()
+# weighted (light-curve) and exposure-corrected branches shard the same way
+from hendrics_b200.io import Lightcurve
+edges = np.arange(8e7, 8e7 + 1000.0 + 1e-3, 5e-3)
+lc = Lightcurve(time=(edges[:-1] + edges[1:]) / 2, counts=np.histogram(ts, bins=edges)[0], gti=ev.gti, dt=5e-3)
+wfull = folding_search(lc, 9.85, 9.95, func=epoch_folding_search, oversample=2, nbin=32)
+wref = epoch_folding_search((lc.time - 8e7).astype(np.float64), wfull[0], nbin=32, weights=lc.counts)
+assert np.array_equal(wfull[1], wref[1]), np.abs(wfull[1] - wref[1]).max()
+xfull = folding_search(ev, 9.85, 9.95, func=z_n_search, oversample=2, nbin=64, nharm=2, expocorr=True)
+xref = z_n_search(t, xfull[0], nharm=2, nbin=64, expocorr=True, gti=(ev.gti - 8e7).astype(np.float64))
+assert np.array_equal(xfull[1], xref[1])
 np.random.seed(0)
 q = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, silent=True)
 os.environ["HX_NO_SHARD"] = "1"
