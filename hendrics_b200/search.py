@@ -94,7 +94,7 @@ def _folding_search(
     dev = _device(device)
     frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
     fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
-    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    grid_shape = (fdots.size, frequencies.size)
     times = np.asanyarray(times)
     if times.size == 0:
         raise ValueError("No events to fold")
@@ -117,8 +117,8 @@ def _folding_search(
 
     freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
     fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
-    stats_d = torch.zeros(fgrid.shape, dtype=torch.float64, device=dev)
-    prof_d = torch.zeros(fgrid.shape + (nbin,), dtype=torch.int64, device=dev) if return_profiles else None
+    stats_d = torch.zeros(grid_shape, dtype=torch.float64, device=dev)
+    prof_d = torch.zeros(grid_shape + (nbin,), dtype=torch.int64, device=dev) if return_profiles else None
     count = 0
     for s in start_times:
         if UPSTREAM_SEMANTICS["drop_last_event"]:
@@ -139,16 +139,23 @@ def _folding_search(
         else:
             stats_d += res
         count += 1
-    stats = stats_d.cpu().numpy()
-    with np.errstate(invalid="ignore", divide="ignore"):
-        stats = stats / count
-    if fgrid.shape[0] == 1:
-        out = (fgrid.flatten(), stats.flatten())
-    else:
-        out = (fgrid, fdgrid, stats)
+    out = _grids_and_stats(frequencies, fdots, stats_d, count)
     if return_profiles:
         out = out + (prof_d.cpu().numpy(),)
     return out
+
+
+def _grids_and_stats(frequencies, fdots, stats_d, count):
+    """Return tuple of upstream's ``_folding_search``: ``(fgrid.flatten(), stats.flatten() / count)`` for a single
+    fdot, else ``(fgrid, fdgrid, stats / count)`` with shape (n_fdot, n_freq).  The division (same IEEE operation as
+    numpy's) runs on the device and the 1-D case skips the meshgrid: no extra host passes over 10^6-trial arrays."""
+    torch = _torch()
+    stats_d = stats_d / count if count > 0 else torch.full_like(stats_d, float("nan"))  # upstream: 0 / 0
+    stats = stats_d.cpu().numpy()
+    if fdots.size == 1:
+        return frequencies, stats.reshape(-1)  # `frequencies` is already this call's own astype() copy
+    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    return fgrid, fdgrid, stats
 
 
 def _is_slow_branch(expocorr, weights):
@@ -197,7 +204,7 @@ def _folding_search_weighted(
     dev = _device(device)
     frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
     fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
-    fgrid, fdgrid = np.meshgrid(frequencies, fdots)
+    grid_shape = (fdots.size, frequencies.size)
     times = np.asanyarray(times)
     if times.size == 0:
         raise ValueError("No events to fold")
@@ -226,8 +233,8 @@ def _folding_search_weighted(
         gti_all = np.asanyarray(gti).astype(np.float64)
     freqs_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
     fdots_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
-    stats_d = torch.zeros(fgrid.shape, dtype=torch.float64, device=dev)
-    prof_d = torch.zeros(fgrid.shape + (nbin,), dtype=torch.float64, device=dev) if return_profiles else None
+    stats_d = torch.zeros(grid_shape, dtype=torch.float64, device=dev)
+    prof_d = torch.zeros(grid_shape + (nbin,), dtype=torch.float64, device=dev) if return_profiles else None
     count = 0
     for s in start_times:
         if UPSTREAM_SEMANTICS["drop_last_event"]:
@@ -256,13 +263,7 @@ def _folding_search_weighted(
         else:
             stats_d += res
         count += 1
-    stats = stats_d.cpu().numpy()
-    with np.errstate(invalid="ignore", divide="ignore"):
-        stats = stats / count
-    if fgrid.shape[0] == 1:
-        out = (fgrid.flatten(), stats.flatten())
-    else:
-        out = (fgrid, fdgrid, stats)
+    out = _grids_and_stats(frequencies, fdots, stats_d, count)
     if return_profiles:
         out = out + (prof_d.cpu().numpy(),)
     return out
