@@ -42,6 +42,8 @@ SIGNATURES = {
     "hx_qffa_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64,
                                   _int, _vp, _vp, _vp]),
     "hx_transient_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _i64, _int, _int, _int, _int, _vp, _vp]),
+    "hx_orbital_search": (_int, [_c_dp, _i64, _dbl, _dbl, _dbl, _dbl, _c_dp, _i64, _int, _int, _c_dp, _c_u32p, _int]),
+    "hx_orbital_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _dbl, _dbl, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "hx_zn_unbinned": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _c_dp, _int]),
     "hx_zn_unbinned_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),

@@ -19,6 +19,7 @@ from __future__ import annotations
 import argparse
 import copy
 import logging
+import os
 import warnings
 
 import numpy as np
@@ -114,6 +115,99 @@ def folding_search(
     elif len(results) == 3:
         frequencies, fdots, stats = results
         return frequencies, fdots, stats, step, fdotstep, length
+
+
+TWOPI = 2 * np.pi
+D_OMEGA_FACTOR = 2 * np.sqrt(3)
+
+
+def _save_df_to_csv(df, csv_file, reset=False):
+    """hendrics/efsearch.py:189-196."""
+    if not os.path.exists(csv_file) or reset:
+        mode, header = "w", True
+    else:
+        mode, header = "a", False
+    df.to_csv(csv_file, header=header, index=False, mode=mode)
+
+
+def decide_binary_parameters(length, freq_range, porb_range, asini_range, fdot_range=[0, 0], NMAX=10,
+                             csv_file="db.csv", reset=False):
+    """hendrics/efsearch.py:208-260: random (freq, fdot, X, Porb) rows for ``folding_orbital_search``."""
+    import pandas as pd
+
+    count = 0
+    omega_range = [1 / porb_range[1], 1 / porb_range[0]]
+    columns = ["freq", "fdot", "X", "Porb", "done", "max_stat", "min_stat", "best_T0"]
+    df = 1 / length
+    log.info(f"Recommended frequency steps: {int(np.diff(freq_range)[0] // df + 1)}")
+    while count < NMAX:
+        if count > 0:  # only the first loop deletes the file
+            reset = False
+        block_of_data = []
+        freq = np.random.uniform(freq_range[0], freq_range[1])
+        fdot = np.random.uniform(fdot_range[0], fdot_range[1])
+        dX = 1 / (TWOPI * freq)
+        nX = int(np.diff(asini_range)[0] // dX) + 1
+        Xs = np.random.uniform(asini_range[0], asini_range[1], nX)
+        for X in Xs:
+            dOmega = 1 / (TWOPI * freq * X * length) * D_OMEGA_FACTOR
+            nOmega = int(np.diff(omega_range)[0] // dOmega) + 1
+            Omegas = np.random.uniform(omega_range[0], omega_range[1], nOmega)
+            for Omega in Omegas:
+                block_of_data.append([freq, fdot, X, TWOPI / Omega, False, 0.0, 0.0, 0.0])
+        df = pd.DataFrame(block_of_data, columns=columns)
+        _save_df_to_csv(df, csv_file, reset=reset)
+        count += 1
+    return csv_file
+
+
+def folding_orbital_search(events, parameter_csv_file, chunksize=100, outfile="out.csv", fun=epoch_folding_search,
+                           **fun_kwargs):
+    """hendrics/efsearch.py:263-310.  For every parameter row the loop over the trial epochs T0 (two demodulation
+    passes + one single-trial search each, :294-302) is ONE launch of ``hx_orbital_search_dev`` when ``fun`` is this
+    package's ``epoch_folding_search`` / ``z_n_search`` with plain keywords; any other ``fun`` is called T0 by T0 like
+    the reference does.  As in the reference the T0s are drawn with ``np.random.uniform`` and chunks whose index does
+    not start at 0 are skipped (``chunk["done"][0]`` raises for them, :274-277)."""
+    import pandas as pd
+
+    from .search import orbital_fold_stats
+
+    times = (events.time - events.gti[0, 0]).astype(np.float64)
+    batched = fun in (epoch_folding_search, z_n_search) and set(fun_kwargs) <= {"nbin", "nharm"}
+    for chunk in pd.read_csv(parameter_csv_file, chunksize=chunksize):
+        try:
+            chunk["done"][0]
+        except Exception:
+            continue
+        for i in range(len(chunk)):
+            if chunk["done"][i]:
+                continue
+            row = chunk.iloc[i]
+            freq, fdot, X, Porb = np.array([row["freq"], row["fdot"], row["X"], row["Porb"]], dtype=np.float64)
+            dT0 = min(1 / (TWOPI**2 * freq) * Porb / X, Porb / 10)
+            max_stats, min_stats, best_T0 = 0, 1e32, None
+            T0s = np.random.uniform(0, Porb, int(Porb // dT0 + 1))
+            if batched:
+                nharm = fun_kwargs.get("nharm", 4) if fun is z_n_search else 0
+                all_stats = orbital_fold_stats(times, freq, fdot, X, Porb, T0s, nbin=fun_kwargs.get("nbin", 128),
+                                               nharm=nharm)
+            else:
+                all_stats = []
+                for T0 in T0s:
+                    new_values = times - X * np.sin(2 * np.pi * (times - T0) / Porb)
+                    new_values = new_values - X * np.sin(2 * np.pi * (new_values - T0) / Porb)
+                    all_stats.append(fun(new_values, np.array([freq]), fdots=fdot, **fun_kwargs)[1][0])
+            for T0, stat in zip(T0s, all_stats):  # the reference's running max / min (:298-302), NaNs never win
+                if stat > max_stats:
+                    max_stats, best_T0 = stat, T0
+                if stat < min_stats:
+                    min_stats = stat
+            idx = chunk.index[i]
+            chunk.iloc[idx, chunk.columns.get_loc("max_stat")] = max_stats
+            chunk.iloc[idx, chunk.columns.get_loc("min_stat")] = min_stats
+            chunk.iloc[idx, chunk.columns.get_loc("best_T0")] = best_T0
+            chunk.iloc[idx, chunk.columns.get_loc("done")] = True
+        _save_df_to_csv(chunk, outfile)
 
 
 def time_intervals_from_gtis(gtis, segment_size, fraction_step=1):

@@ -18,7 +18,8 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "fold_profiles_weighted", "z_n_search_unbinned",
+__all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "fold_profiles_weighted", "orbital_fold_stats",
+           "z_n_search_unbinned",
            "UPSTREAM_SEMANTICS"]
 
 # The two places where the restatement of stingray's `_folding_search` could not be checked against
@@ -345,6 +346,28 @@ def fold_profiles_weighted(times, frequencies, fdots=0, nbin=128, nharm=0, weigh
         stop_time=times[-1] + np.abs(times[1] - times[0]), want_profiles=True,
     )
     return stats.cpu().numpy(), prof.cpu().numpy()
+
+
+def orbital_fold_stats(times, freq, fdot, X, Porb, T0s, nbin=128, nharm=0, device=None, return_profiles=False):
+    """Statistic of the single trial ``(freq, fdot)`` on the event times demodulated for every trial epoch of
+    ascending node in ``T0s`` (``hx_orbital_search_dev``): the T0 loop of hendrics/efsearch.py:294-302 in one launch.
+    ``nharm == 0``: epoch-folding chi^2, else Z^2_nharm.  Returns ``stats[len(T0s)]`` (and the uint32 profiles)."""
+    torch = _torch()
+    dev = _device(device)
+    ts_d = _aligned(torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(dev))
+    t0_d = torch.from_numpy(np.ascontiguousarray(np.atleast_1d(T0s), dtype=np.float64)).to(dev)
+    stats = torch.empty(t0_d.numel(), dtype=torch.float64, device=dev)
+    prof = torch.empty((t0_d.numel(), nbin), dtype=torch.int32, device=dev) if return_profiles else None
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().hx_orbital_search_dev(
+            ts_d.data_ptr(), ts_d.numel(), float(freq), float(fdot), float(X), float(Porb), t0_d.data_ptr(),
+            t0_d.numel(), int(nbin), int(nharm), stats.data_ptr(), prof.data_ptr() if return_profiles else None,
+            torch.cuda.current_stream().cuda_stream,
+        )
+    _cabi.check(rc)
+    if return_profiles:
+        return stats.cpu().numpy(), (prof.to(torch.int64) & 0xFFFFFFFF).cpu().numpy()
+    return stats.cpu().numpy()
 
 
 def z_n_search_unbinned(times, frequencies, nharm=2, fdots=0, device=None):

@@ -139,6 +139,20 @@ int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_firs
                             const double *mean_f, const double *mean_fd, int64_t n_centres, int nbin, int nprof,
                             int nharm, int n_levels, double *d_stats, void *stream);
 
+/* ---- orbital-demodulation fold (widening) -------------------------------
+ * Replaces the T0 loop of hendrics/efsearch.py:294-302 (folding_orbital_search): for every trial epoch of ascending
+ * node T0[k], demodulate the event times twice (:295-296), then run the fast branch of
+ * epoch_folding_search / z_n_search on them for the single trial (freq, fdot) (:297).
+ *   times [n_ev] (as folding_orbital_search computes them: events.time - gti[0, 0]);  stats [n_t0];
+ *   profiles [n_t0 * nbin] uint32 or NULL.  nharm == 0: epoch-folding chi^2, else Z^2_nharm.
+ * sin() is CUDA's, not numpy's: statistics agree to ~1e-6 (isolated +-1 bin moves), not bit for bit. */
+int hx_orbital_search(const double *times, int64_t n_ev, double freq, double fdot, double X, double Porb,
+                      const double *T0, int64_t n_t0, int nbin, int nharm, double *stats, uint32_t *profiles,
+                      int device);
+int hx_orbital_search_dev(const double *d_times, int64_t n_ev, double freq, double fdot, double X, double Porb,
+                          const double *d_T0, int64_t n_t0, int nbin, int nharm, double *d_stats, uint32_t *d_profiles,
+                          void *stream);
+
 /* ---- K4: unbinned Z^2_n (extension; oracle formula hendrics/efsearch.py:366-404) ---------
  * stats[i*n_f + j] = 2/N * sum_{k=1..nharm} [(sum cos 2 pi k phi)^2 + (sum sin 2 pi k phi)^2]
  * with phi = frac(t*f + 0.5*t*t*fd) per event.

@@ -568,6 +568,31 @@ def folding_search(
 
 
 # --------------------------------------------------------------------------------------
+# hendrics/efsearch.py:263-310 folding_orbital_search (T0 loop of one parameter row)
+# --------------------------------------------------------------------------------------
+def orbital_demodulate(times, T0, X, Porb):
+    """efsearch.py:295-296: two fixed-point iterations of the Roemer-delay removal."""
+    new_values = times - X * np.sin(2 * np.pi * (times - T0) / Porb)
+    new_values = new_values - X * np.sin(2 * np.pi * (new_values - T0) / Porb)
+    return new_values
+
+
+def orbital_stats(times, freq, fdot, X, Porb, T0s, fun=None, return_profiles=False, **fun_kwargs):
+    """efsearch.py:294-302: ``fun(new_values, np.array([freq]), fdots=fdot, **fun_kwargs)[1][0]`` for every T0."""
+    if fun is None:
+        fun = epoch_folding_search
+    stats = np.zeros(len(T0s))
+    profs = []
+    for k, T0 in enumerate(T0s):
+        nv = orbital_demodulate(times, T0, X, Porb)
+        res = fun(nv, np.array([freq]), fdots=fdot, return_profiles=return_profiles, **fun_kwargs)
+        stats[k] = res[1][0]
+        if return_profiles:
+            profs.append(res[2][0, 0])
+    return (stats, np.array(profs)) if return_profiles else stats
+
+
+# --------------------------------------------------------------------------------------
 # --fast ("quasi-fast folding")
 # --------------------------------------------------------------------------------------
 ONE_SIXTH = 1 / 6
