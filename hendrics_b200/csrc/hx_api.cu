@@ -20,6 +20,11 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+std::recursive_mutex &api_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 // Shared-window address at which dynamic shared memory starts for a kernel without static
 // shared memory (the fold kernel aligns its histogram blocks on absolute shared addresses).
 __global__ void probe_smem_base_kernel(uint32_t *out) {

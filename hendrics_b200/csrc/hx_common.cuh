@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "../../include/hx_search.h"
@@ -15,6 +16,9 @@ namespace hx {
 // ---- error plumbing ------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// The library keeps per-device planning / timing state (last-kernel events, tuning hooks): compute entry points
+// serialise on this lock, so concurrent calls from several host threads are safe (they run one after the other).
+std::recursive_mutex &api_mutex();
 
 #define HX_CUDA_TRY(expr)                                                                   \
     do {                                                                                    \

@@ -612,6 +612,7 @@ int device_ranges(const double *d_times, int64_t n_ev, const double *d_freqs, in
 int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
                          const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
                          uint32_t *d_profiles, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_times || !d_freqs || !d_fdots || !d_stats) {
         set_error("hx_fold_search: null pointer argument");
         return HX_ERR_ARG;

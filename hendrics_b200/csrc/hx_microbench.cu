@@ -199,11 +199,61 @@ __global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a,
     if (s == 0xffffffffu) atomicAdd(out, 1u);
 }
 
+// kinds 13/14: where should the broadcast event stream come from?  K1's f-only loop at K1's occupancy for nbin = 128
+// (R = 2, 4 warps per CTA, ~72 KB of shared memory per CTA), events read with broadcast LDS.128 from a shared-memory
+// tile (kind 13, today's K1) or with indexed LDC.64 from a __constant__ array (kind 14): constant loads do not go through
+// the shared-memory data pipe that bounds the f-only kernels.
+__constant__ double mb_const_events[4096];
+
+template <bool FROM_CONST>
+__global__ void __launch_bounds__(128) mb_evsrc_kernel(uint32_t *out, double a) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const uint32_t base = smem_u32(dsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NEV = 512;
+    double *tile = reinterpret_cast<double *>(dsm);
+    const uint32_t hist = base + NEV * 8;
+    uint32_t cb[2];
+    for (int r = 0; r < 2; r++) {
+        cb[r] = hist + (uint32_t)(warp * 2 + r) * 8192u + lane * 4u;
+        for (int j = 0; j < 64; j++) sts_u32(cb[r] + j * 128, 0u);
+    }
+    for (int i = threadIdx.x; i < NEV; i += blockDim.x) tile[i] = 1000.0 + 0.37 * i;
+    __syncthreads();
+    const double f[2] = {a * (1.0 + 1e-6 * (threadIdx.x + 1)) * 16384.0, a * (1.0 + 1e-6 * (threadIdx.x + 129)) * 16384.0};
+    for (int it = 0; it < MB_ITERS / 32; it++) {
+#pragma unroll 2
+        for (int e = 0; e < NEV; e += 4) {
+            double t[4];
+            if (FROM_CONST) {
+                const int o = (e + it * 4) & 4092;
+#pragma unroll
+                for (int u = 0; u < 4; u++) t[u] = mb_const_events[o + u];
+            } else {
+                const double2 t01 = *reinterpret_cast<const double2 *>(tile + e), t23 = *reinterpret_cast<const double2 *>(tile + e + 2);
+                t[0] = t01.x, t[1] = t01.y, t[2] = t23.x, t[3] = t23.y;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint32_t lo = (uint32_t)__double2loint(__dadd_rd(__dmul_rn(t[u], f[r]), HX_MAGIC));
+                    red_shared_add_u32((lo & 0x1f80u) | cb[r], (lo & 0x2000u) | 1u);
+                }
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    for (int r = 0; r < 2; r++)
+        for (int j = 0; j < 64; j++) s += lds_u32(cb[r] + j * 128) & 0x1fffu;
+    if (s == 0xffffffffu) atomicAdd(out, 1u);
+}
+
 }  // namespace hx
 
 extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) {
     using namespace hx;
-    if (!ops_per_s || kind < 0 || kind > 12 || reps < 1) {
+    if (!ops_per_s || kind < 0 || kind > 14 || reps < 1) {
         set_error("hx_microbench: bad arguments");
         return HX_ERR_ARG;
     }
@@ -224,6 +274,13 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     if (kind == 3) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (kind == 11) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     if (kind == 12) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 13) HX_CUDA_TRY(cudaFuncSetAttribute(mb_evsrc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 14) {
+        HX_CUDA_TRY(cudaFuncSetAttribute(mb_evsrc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        std::vector<double> ev(4096);
+        for (int i = 0; i < 4096; i++) ev[i] = 1000.0 + 0.37 * i;
+        HX_CUDA_TRY(cudaMemcpyToSymbol(mb_const_events, ev.data(), ev.size() * sizeof(double)));
+    }
     double best_ms = 1e30;
     for (int r = 0; r < reps + 1; r++) {  // first rep is a warm-up
         HX_CUDA_TRY(cudaEventRecord(e0));
@@ -240,7 +297,9 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
             case 9: mb_mix_f2i_kernel<6><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
             case 10: mb_mix_f2i_kernel<8><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
             case 11: mb_rowcta_kernel<false><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
-            default: mb_rowcta_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            case 12: mb_rowcta_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            case 13: mb_evsrc_kernel<false><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9); break;
+            default: mb_evsrc_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9); break;
         }
         HX_CHECK_LAUNCH("microbench kernel");
         HX_CUDA_TRY(cudaEventRecord(e1));
@@ -261,6 +320,10 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
                       : (kind == 1) ? (double)MB_ITERS * MB_ILP * 2
                       : (kind >= 4) ? (double)MB_ITERS * MB_ILP  // units (event*trial equivalents; kind 6: F2I)
                                     : (double)MB_ITERS * 4;
+    if (kind >= 13) {
+        *ops_per_s = (double)(MB_ITERS / 32) * 512 * 2 * 128 * (double)(di.sm_count * 6) / (best_ms * 1e-3);
+        return HX_OK;
+    }
     if (kind >= 11) {
         *ops_per_s = (double)(MB_ITERS / 32) * 256 * 2 * 128 * (double)(di.sm_count * 6) / (best_ms * 1e-3);
         return HX_OK;

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) orbital_stat_kernel(const uint32_t *__res
 int orbital_search_dev_impl(const double *d_times, int64_t n_ev, double freq, double fdot, double X, double Porb,
                             const double *d_T0, int64_t n_t0, int nbin, int nharm, double *d_stats,
                             uint32_t *d_profiles, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_times || !d_T0 || !d_stats) {
         set_error("hx_orbital_search: null pointer argument");
         return HX_ERR_ARG;

@@ -1067,6 +1067,7 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
                          const double *mean_fd, const double *mean_fdd, int64_t n_centres, int nbin, int nprof,
                          const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
                          uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_t || !mean_f || !mean_fd || !mean_fdd || !L || !Q || !d_stats) {
         set_error("hx_qffa_search: null pointer argument");
         return HX_ERR_ARG;

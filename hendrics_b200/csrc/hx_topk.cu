@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(1024) topk_final_kernel(const Cand *block_in, 
 
 int topk_dev_impl(const double *d_stats, int64_t n, int k, int64_t *h_idx, double *h_val, int64_t *n_out,
                   cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_stats || !h_idx || !h_val || !n_out || n < 0 || k < 0 || k > 4096) {
         set_error("hx_topk: bad arguments");
         return HX_ERR_ARG;

@@ -433,6 +433,7 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
                           const double *d_freqs, int64_t n_f, const double *d_fdots, int64_t n_fd, int nbin,
                           int nharm, const double *h_gti, int64_t n_gti, double start_time, double stop_time,
                           double *d_stats, double *d_profiles, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_times || !d_freqs || !d_fdots || !d_stats) {
         set_error("hx_wfold_search: null pointer argument");
         return HX_ERR_ARG;

@@ -134,6 +134,7 @@ static zn_fn_t pick_zn(int nh, bool fd) {
 
 int zn_unbinned_dev_impl(const double *d_t, int64_t n_ev, const double *d_f, int64_t n_f, const double *d_fd,
                          int64_t n_fd, int nharm, double *d_stats, bool has_fd, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_t || !d_f || !d_fd || !d_stats || n_ev < 0 || n_f < 0 || n_fd < 0) {
         set_error("hx_zn_unbinned: bad arguments");
         return HX_ERR_ARG;

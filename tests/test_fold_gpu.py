@@ -324,3 +324,34 @@ def test_error_paths():
     # the library stays usable after an error
     s, _ = _host_call(ts, f, [0.0], 16, 0)
     assert np.isfinite(s).all()
+
+
+def test_concurrent_calls_from_host_threads():
+    """The library serialises its entry points: searches issued from several host threads give the single-thread
+    results (the reference makes no re-entrancy promise; this one does)."""
+    import threading
+
+    from hendrics_b200 import epoch_folding_search, z_n_search
+
+    ts = _events(30000, 500.0, 13)
+    freqs = np.arange(9.8, 10.0, 0.0005)
+    want_z = z_n_search(ts, freqs, nharm=2, nbin=64)[1]
+    want_e = epoch_folding_search(ts, freqs, nbin=16, fdots=[0.0, 1e-6])[2]
+    out, errs = {}, []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                if k % 2:
+                    out[k] = z_n_search(ts, freqs, nharm=2, nbin=64)[1]
+                else:
+                    out[k] = epoch_folding_search(ts, freqs, nbin=16, fdots=[0.0, 1e-6])[2]
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for k in range(4):
+        assert np.array_equal(out[k], want_z if k % 2 else want_e)
