@@ -36,7 +36,7 @@ SIGNATURES = {
                                _c_dp, _c_dp, _int]),
     "hx_wfold_search_dev": (_int, [_vp, _vp, _dbl, _i64, _vp, _i64, _vp, _i64, _int, _int, _c_dp, _i64, _dbl, _dbl,
                                    _vp, _vp, _vp]),
-    "hx_wfold_last_kernel_ms": (_int, [_c_dp, ctypes.POINTER(_int)]),
+    "hx_wfold_last_kernel_ms": (_int, [_c_dp, ctypes.POINTER(_int), _c_i64p]),
     "hx_qffa_search": (_int, [_c_dp, _i64, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64, _int, _c_dp,
                               _c_u32p, _int]),
     "hx_qffa_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64,
@@ -135,11 +135,11 @@ def fold_last_kernel():
 
 
 def wfold_last_kernel():
-    """(ms, cell kind) of the K1w launches of the most recent weighted fold: 0 fp64 cells, 1 u32 (integer
-    weights), 2 u32 (no weight array)."""
-    ms, k = _dbl(0.0), _int(-1)
-    check(lib().hx_wfold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(k)))
-    return ms.value, k.value
+    """(ms, cell kind, events folded) of the K1w launches of the most recent weighted fold: 0 fp64 cells, 1 u32
+    (integer weights), 2 u32 (no weight array); events folded < n when zero-weight entries were dropped."""
+    ms, k, n = _dbl(0.0), _int(-1), _i64(0)
+    check(lib().hx_wfold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(k), ctypes.byref(n)))
+    return ms.value, k.value, n.value
 
 
 def qffa_last_kernel():

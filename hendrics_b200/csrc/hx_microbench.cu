@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) mb_mix_f2i_kernel(uint32_t *out, double a
 //   kind 11 (PRE = false): tt = t*t and m2 = tt*fdh computed per event and thread (4 FP64 ops per unit; today's K1)
 //   kind 12 (PRE = true):  m2 read from a second tile, precomputed once per CTA (3 FP64 ops per unit, one more
 //                          shared-memory wavefront per event and warp)
-template <bool PRE>
+template <bool PRE, int R>
 __global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a, double b) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const uint32_t base = smem_u32(dsm);
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a,
     double *tile = reinterpret_cast<double *>(dsm);        // [NEV] times
     double *mtile = tile + NEV;                             // [NEV] fdot terms
     const uint32_t hist = base + 2 * NEV * 8;
-    uint32_t cb[2];
-    for (int r = 0; r < 2; r++) {
-        cb[r] = hist + (uint32_t)(warp * 2 + r) * 8192u + lane * 4u;  // 64 words x 128 B per column (packed nbin = 128)
+    uint32_t cb[R];
+    for (int r = 0; r < R; r++) {
+        cb[r] = hist + (uint32_t)(warp * R + r) * 8192u + lane * 4u;  // 64 words x 128 B per column (packed nbin = 128)
         for (int j = 0; j < 64; j++) sts_u32(cb[r] + j * 128, 0u);
     }
     for (int i = threadIdx.x; i < NEV; i += blockDim.x) {
@@ -165,24 +165,31 @@ __global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a,
         mtile[i] = (1000.0 + 0.37 * i) * (1000.0 + 0.37 * i) * b;
     }
     __syncthreads();
-    const double f[2] = {a * (1.0 + 1e-6 * (threadIdx.x + 1)) * 16384.0, a * (1.0 + 1e-6 * (threadIdx.x + 129)) * 16384.0};
+    double f[R];
+    for (int r = 0; r < R; r++) f[r] = a * (1.0 + 1e-6 * (threadIdx.x + 1 + 128 * r)) * 16384.0;
     const double fdh = b * 16384.0;
+    constexpr int UE = R >= 4 ? 2 : 4;
     for (int it = 0; it < MB_ITERS / 32; it++) {
 #pragma unroll 2
-        for (int e = 0; e < NEV; e += 4) {
-            const double2 t01 = *reinterpret_cast<const double2 *>(tile + e), t23 = *reinterpret_cast<const double2 *>(tile + e + 2);
-            double t[4] = {t01.x, t01.y, t23.x, t23.y}, m[4];
-            if (PRE) {
-                const double2 m01 = *reinterpret_cast<const double2 *>(mtile + e), m23 = *reinterpret_cast<const double2 *>(mtile + e + 2);
-                m[0] = m01.x, m[1] = m01.y, m[2] = m23.x, m[3] = m23.y;
-            } else {
+        for (int e = 0; e < NEV; e += UE) {
+            double t[UE], m[UE];
 #pragma unroll
-                for (int u = 0; u < 4; u++) m[u] = __dmul_rn(__dmul_rn(t[u], t[u]), fdh);
+            for (int u = 0; u < UE; u += 2) {
+                const double2 tv = *reinterpret_cast<const double2 *>(tile + e + u);
+                t[u] = tv.x, t[u + 1] = tv.y;
+                if (PRE) {
+                    const double2 mv = *reinterpret_cast<const double2 *>(mtile + e + u);
+                    m[u] = mv.x, m[u + 1] = mv.y;
+                }
+            }
+            if (!PRE) {
+#pragma unroll
+                for (int u = 0; u < UE; u++) m[u] = __dmul_rn(__dmul_rn(t[u], t[u]), fdh);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < UE; u++)
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
+                for (int r = 0; r < R; r++) {
                     const double y = __dadd_rd(__dadd_rn(__dmul_rn(t[u], f[r]), m[u]), HX_MAGIC);
                     const uint32_t lo = (uint32_t)__double2loint(y);
                     red_shared_add_u32((lo & 0x1f80u) | cb[r], (lo & 0x2000u) | 1u);
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(128) mb_rowcta_kernel(uint32_t *out, double a,
     }
     __syncthreads();
     uint32_t s = 0;
-    for (int r = 0; r < 2; r++)
+    for (int r = 0; r < R; r++)
         for (int j = 0; j < 64; j++) {
             const uint32_t v = lds_u32(cb[r] + j * 128);
             s += (v & 0x1fffu);
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(128) mb_evsrc_kernel(uint32_t *out, double a) 
 
 extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) {
     using namespace hx;
-    if (!ops_per_s || kind < 0 || kind > 14 || reps < 1) {
+    if (!ops_per_s || kind < 0 || kind > 16 || reps < 1) {
         set_error("hx_microbench: bad arguments");
         return HX_ERR_ARG;
     }
@@ -272,8 +279,10 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
     const size_t smem = (kind >= 4) ? (size_t)(threads / 32) * 2048 : (kind >= 2) ? (size_t)(threads / 32) * 4 * 2048 : 0;
     if (kind == 2) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (kind == 3) HX_CUDA_TRY(cudaFuncSetAttribute(mb_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (kind == 11) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    if (kind == 12) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 11) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 12) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 15) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    if (kind == 16) HX_CUDA_TRY(cudaFuncSetAttribute(mb_rowcta_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     if (kind == 13) HX_CUDA_TRY(cudaFuncSetAttribute(mb_evsrc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     if (kind == 14) {
         HX_CUDA_TRY(cudaFuncSetAttribute(mb_evsrc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
@@ -296,10 +305,12 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
             case 8: mb_mix_f2i_kernel<4><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
             case 9: mb_mix_f2i_kernel<6><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
             case 10: mb_mix_f2i_kernel<8><<<grid, threads, smem>>>(out.as<uint32_t>(), 1.0000001, 1e-9); break;
-            case 11: mb_rowcta_kernel<false><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
-            case 12: mb_rowcta_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            case 11: mb_rowcta_kernel<false, 2><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            case 12: mb_rowcta_kernel<true, 2><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
             case 13: mb_evsrc_kernel<false><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9); break;
-            default: mb_evsrc_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9); break;
+            case 14: mb_evsrc_kernel<true><<<di.sm_count * 3 * 2, 128, 72 * 1024>>>(out.as<uint32_t>(), 9.9); break;
+            case 15: mb_rowcta_kernel<false, 4><<<di.sm_count * 3 * 2, 64, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
+            default: mb_rowcta_kernel<true, 4><<<di.sm_count * 3 * 2, 64, 72 * 1024>>>(out.as<uint32_t>(), 9.9, 1e-10); break;
         }
         HX_CHECK_LAUNCH("microbench kernel");
         HX_CUDA_TRY(cudaEventRecord(e1));
@@ -320,6 +331,10 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
                       : (kind == 1) ? (double)MB_ITERS * MB_ILP * 2
                       : (kind >= 4) ? (double)MB_ITERS * MB_ILP  // units (event*trial equivalents; kind 6: F2I)
                                     : (double)MB_ITERS * 4;
+    if (kind >= 15) {  // 64 threads x 4 trials
+        *ops_per_s = (double)(MB_ITERS / 32) * 256 * 4 * 64 * (double)(di.sm_count * 6) / (best_ms * 1e-3);
+        return HX_OK;
+    }
     if (kind >= 13) {
         *ops_per_s = (double)(MB_ITERS / 32) * 512 * 2 * 128 * (double)(di.sm_count * 6) / (best_ms * 1e-3);
         return HX_OK;

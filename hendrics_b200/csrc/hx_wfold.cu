@@ -35,6 +35,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cub/device/device_select.cuh>
+
 #include "hx_common.cuh"
 
 namespace hx {
@@ -257,11 +259,12 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
     }
 }
 
-// fp64 weights -> uint32 when every one of them is a non-negative integer; flags[0] = 1 otherwise,
-// flags[1..2] = the 64-bit sum of the integer weights (the u32 cells need it below 2^32)
+// One pass over the weights: uint32 copies when every weight is a non-negative integer (flags[0] = 1 otherwise),
+// flags[1] = the 64-bit sum of the integer weights (the u32 cells need it below 2^32), keep[i] = (w[i] != 0) and
+// flags[2] = the number of non-zero weights (a light curve at fine time resolution is mostly empty bins).
 __global__ void wfold_intweights_kernel(const double *__restrict__ w, long long n, uint32_t *__restrict__ out,
-                                        unsigned long long *flags) {
-    unsigned long long sum = 0;
+                                        unsigned char *__restrict__ keep, unsigned long long *flags) {
+    unsigned long long sum = 0, nnz = 0;
     bool bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double v = w[i];
@@ -270,10 +273,29 @@ __global__ void wfold_intweights_kernel(const double *__restrict__ w, long long 
         const uint32_t u = ok ? (uint32_t)v : 0u;
         out[i] = u;
         sum += u;
+        const bool k = !(v == 0.0);  // NaN weights are kept (and poison the profile, as upstream)
+        keep[i] = k;
+        nnz += k;
     }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+    }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(flags, 1ull);
     if ((threadIdx.x & 31) == 0 && sum) atomicAdd(flags + 1, sum);
+    if ((threadIdx.x & 31) == 0 && nnz) atomicAdd(flags + 2, nnz);
+}
+
+// stable stream compaction of `in[n]` by `keep` into `out` (cub::DeviceSelect::Flagged); *d_count receives the count
+template <typename T>
+static int compact_flagged(const T *in, const unsigned char *keep, T *out, int *d_count, int n, cudaStream_t st) {
+    size_t tmp_bytes = 0;
+    HX_CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, in, keep, out, d_count, n, st));
+    AsyncBuf tmp(st);
+    HX_CUDA_TRY(tmp.alloc(tmp_bytes));
+    HX_CUDA_TRY(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, in, keep, out, d_count, n, st));
+    count_launch(2);
+    return HX_OK;
 }
 
 // ---- exposure correction -------------------------------------------------------------------------
@@ -307,12 +329,20 @@ __device__ __forceinline__ double phase_raw(double t, double f, double fdh, bool
     return x;
 }
 
-// stingray.pulse.pulsar.phase_exposure(start_phase, stop_phase, 1, nbin, gti=gti_phases)[j] before the
-// final normalisation, for one trial and one bin: the per-bin sequence of fp64 accumulations is upstream's.
-__device__ double expo_bin(int j, int nbin, const double *edges, const double *gti, int n_gti, double f, double fdh,
-                           bool has_fd, double start_ph, double stop_ph) {
-    double e = 0.0;
-    const dd p0 = {edges[j], 0.0}, p1 = {edges[j + 1], 0.0};
+// stingray.pulse.pulsar.phase_exposure(start_phase, stop_phase, 1, nbin, gti=gti_phases)[j0 .. j0 + EB) before the final
+// normalisation, for one trial: the per-bin sequence of fp64 accumulations is upstream's (per GTI: + nper / nbin, then
+// + the overlap with each of the one or two fractional limits).  EB bins are kept in registers per pass over the GTIs,
+// so the per-GTI quantities are set up nbin / EB times per trial instead of nbin times.
+constexpr int EB = 8;
+__device__ __forceinline__ void expo_bins(double (&e)[EB], int j0, int nbin, const double *edges, const double *gti, int n_gti,
+                                          double f, double fdh, bool has_fd, double start_ph, double stop_ph) {
+    dd p0[EB], p1[EB];
+#pragma unroll
+    for (int k = 0; k < EB; k++) {
+        e[k] = 0.0;
+        const int j = min(j0 + k, nbin - 1);
+        p0[k] = dd{edges[j], 0.0}, p1[k] = dd{edges[j + 1], 0.0};
+    }
     for (int g = 0; g < n_gti; g++) {
         double g0 = phase_raw(gti[2 * g], f, fdh, has_fd), g1 = phase_raw(gti[2 * g + 1], f, fdh, has_fd);
         if (!(g0 < stop_ph && g1 > start_ph)) continue;
@@ -325,7 +355,7 @@ __device__ double expo_bin(int j, int nbin, const double *edges, const double *g
             if (length.hi > 0.0 && length.lo < 0.0) nper -= 1.0;
             if (length.hi < 0.0 && length.lo > 0.0) nper += 1.0;
         }
-        e = __dadd_rn(e, __ddiv_rn(nper, (double)nbin));
+        const double whole = __ddiv_rn(nper, (double)nbin);
         const double sp = __dsub_rn(g0, trunc(g0));                      // fmod(g0, 1), exact
         const dd frac = two_sum(__dsub_rn(length.hi, nper), length.lo);  // nraw - nper, exact
         const dd endp = dd_add(frac, dd{sp, 0.0});
@@ -339,14 +369,17 @@ __device__ double expo_bin(int j, int nbin, const double *edges, const double *g
         } else {
             l0[0] = dd{sp, 0.0}, l1[0] = endp;
         }
-        for (int k = 0; k < nl; k++) {
-            if (!(dd_le(p0, l1[k]) && dd_le(l0[k], p1))) continue;
-            const dd w = dd_add(dd_min(p1, l1[k]), dd_neg(dd_max(p0, l0[k])));
-            const dd s = two_sum(e, w.hi);
-            e = __dadd_rn(s.hi, __dadd_rn(s.lo, w.lo));
+#pragma unroll
+        for (int k = 0; k < EB; k++) {
+            e[k] = __dadd_rn(e[k], whole);
+            for (int q = 0; q < nl; q++) {
+                if (!(dd_le(p0[k], l1[q]) && dd_le(l0[q], p1[k]))) continue;
+                const dd w = dd_add(dd_min(p1[k], l1[q]), dd_neg(dd_max(p0[k], l0[q])));
+                const dd s = two_sum(e[k], w.hi);
+                e[k] = __dadd_rn(s.hi, __dadd_rn(s.lo, w.lo));
+            }
         }
     }
-    return e;
 }
 
 // scratch[slot][j] /= expo[j] / max(expo), one thread per trial slot (lane-minor layout => coalesced)
@@ -367,10 +400,15 @@ __global__ void __launch_bounds__(128) wfold_expo_kernel(double *__restrict__ sc
     const double start_ph = phase_raw(start_time, f, fdh, has_fd), stop_ph = phase_raw(stop_time, f, fdh, has_fd);
     const size_t base = (size_t)(l >> 5) * nbin * 32 + (l & 31);
     double emax = -INFINITY;
-    for (int j = 0; j < nbin; j++) {
-        const double e = expo_bin(j, nbin, edges, gti, n_gti, f, fdh, has_fd != 0, start_ph, stop_ph);
-        expo[base + (size_t)j * 32] = e;
-        emax = fmax(emax, e);
+    for (int j0 = 0; j0 < nbin; j0 += EB) {
+        double e[EB];
+        expo_bins(e, j0, nbin, edges, gti, n_gti, f, fdh, has_fd != 0, start_ph, stop_ph);
+#pragma unroll
+        for (int k = 0; k < EB; k++)
+            if (j0 + k < nbin) {
+                expo[base + (size_t)(j0 + k) * 32] = e[k];
+                emax = fmax(emax, e[k]);
+            }
     }
     for (int j = 0; j < nbin; j++) {
         const double en = __ddiv_rn(expo[base + (size_t)j * 32], emax);
@@ -428,6 +466,7 @@ static cudaEvent_t g_wev0[64], g_wev1[64];
 static bool g_wev_ok[64] = {false};
 static int g_wlast_device = -1;
 static int g_wlast_cell = -1;
+static long long g_wlast_n_used = 0;  // events actually folded by the last call (after dropping zero weights)
 
 int wfold_search_dev_impl(const double *d_times, const double *d_weights, double unit_weight, int64_t n_ev,
                           const double *d_freqs, int64_t n_f, const double *d_fdots, int64_t n_fd, int nbin,
@@ -469,21 +508,41 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
         return HX_ERR_RANGE;
     }
     // ---- cell type: u32 counters when the weights are integers (or absent), fp64 cells otherwise
-    AsyncBuf b_wi(st), b_flags(st);
+    AsyncBuf b_wi(st), b_flags(st), b_keep(st), b_tc(st), b_wc(st);
     int cell = d_weights ? CELL_F64 : CELL_UNIT;
     const void *d_wt = d_weights;
-    if (d_weights && n_ev > 0 && !(g_wfold_force_generic & 2)) {
+    const double *d_ev = d_times;  // the event stream the fold kernel reads (compacted below when most weights are 0)
+    int64_t n_use = n_ev;
+    if (d_weights && n_ev > 0) {
         HX_CUDA_TRY(b_wi.alloc((size_t)n_ev * sizeof(uint32_t)));
-        HX_CUDA_TRY(b_flags.alloc(2 * sizeof(unsigned long long)));
-        HX_CUDA_TRY(cudaMemsetAsync(b_flags.p, 0, 2 * sizeof(unsigned long long), st));
+        HX_CUDA_TRY(b_keep.alloc((size_t)n_ev));
+        HX_CUDA_TRY(b_flags.alloc(4 * sizeof(unsigned long long)));
+        HX_CUDA_TRY(cudaMemsetAsync(b_flags.p, 0, 4 * sizeof(unsigned long long), st));
         wfold_intweights_kernel<<<(int)std::min<long long>((n_ev + 255) / 256, 1184), 256, 0, st>>>(
-            d_weights, n_ev, b_wi.as<uint32_t>(), b_flags.as<unsigned long long>());
+            d_weights, n_ev, b_wi.as<uint32_t>(), b_keep.as<unsigned char>(), b_flags.as<unsigned long long>());
         HX_CHECK_LAUNCH("wfold_intweights_kernel");
-        unsigned long long hf[2];
+        unsigned long long hf[3];
         HX_CUDA_TRY(cudaMemcpyAsync(hf, b_flags.p, sizeof(hf), cudaMemcpyDeviceToHost, st));
         HX_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hf[0] == 0 && hf[1] < 4294967296ull) cell = CELL_U32, d_wt = b_wi.p;
+        if (hf[0] == 0 && hf[1] < 4294967296ull && !(g_wfold_force_generic & 2)) cell = CELL_U32, d_wt = b_wi.p;
+        // Adding a zero weight changes nothing (upstream's np.histogram adds it all the same): when at least a
+        // quarter of the weights are zero -- empty light-curve bins -- fold only the others.  The compaction is
+        // stable, so fp64 sums keep their order.
+        const long long nnz = (long long)hf[2];
+        if (nnz < n_ev - n_ev / 4 && n_ev < 2147483647LL && !(g_wfold_force_generic & 4)) {
+            int *d_count = reinterpret_cast<int *>(b_flags.as<unsigned long long>() + 3);
+            HX_CUDA_TRY(b_tc.alloc((size_t)std::max<long long>(nnz, 2) * 8));
+            HX_CUDA_TRY(b_wc.alloc((size_t)std::max<long long>(nnz, 2) * 8));
+            if ((rc = compact_flagged(d_times, b_keep.as<unsigned char>(), b_tc.as<double>(), d_count, (int)n_ev, st))) return rc;
+            if (cell == CELL_U32)
+                rc = compact_flagged(b_wi.as<uint32_t>(), b_keep.as<unsigned char>(), b_wc.as<uint32_t>(), d_count, (int)n_ev, st);
+            else
+                rc = compact_flagged(d_weights, b_keep.as<unsigned char>(), b_wc.as<double>(), d_count, (int)n_ev, st);
+            if (rc) return rc;
+            d_ev = b_tc.as<double>(), d_wt = b_wc.p, n_use = nnz;
+        }
     }
+    g_wlast_n_used = n_use;
     const bool f64 = cell == CELL_F64;
     const int shift = f64 ? 8 : 7;
     const bool pow2 = (nbin & (nbin - 1)) == 0;
@@ -549,13 +608,13 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
     const long long slots = (long long)di.sm_count * ctas_per_sm;
     // split the events so that the grid fills at least ~4 waves of CTA slots
     long long ev_splits = 1;
-    if (n_ev > 0 && n_cta_x < 4 * slots) {
-        ev_splits = std::min<long long>((4 * slots + n_cta_x - 1) / n_cta_x, std::max<long long>(1, n_ev / (4 * WTILE_EV)));
+    if (n_use > 0 && n_cta_x < 4 * slots) {
+        ev_splits = std::min<long long>((4 * slots + n_cta_x - 1) / n_cta_x, std::max<long long>(1, n_use / (4 * WTILE_EV)));
         ev_splits = std::min<long long>(std::max<long long>(ev_splits, 1), 65535);
     }
-    long long ev_per_split = (n_ev + ev_splits - 1) / ev_splits;
+    long long ev_per_split = (n_use + ev_splits - 1) / ev_splits;
     ev_per_split = std::max<long long>(WTILE_EV, (ev_per_split + WTILE_EV - 1) / WTILE_EV * WTILE_EV);
-    ev_splits = std::max<long long>(1, (n_ev + ev_per_split - 1) / ev_per_split);
+    ev_splits = std::max<long long>(1, (n_use + ev_per_split - 1) / ev_per_split);
 
     // ---- device temporaries
     AsyncBuf b_tab(st), b_scratch(st), b_expo(st), b_edges(st), b_gti(st);
@@ -579,7 +638,7 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
     }
 
     WFoldArgs a{};
-    a.ev = d_times, a.wt = d_wt, a.n_ev = n_ev, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots;
+    a.ev = d_ev, a.wt = d_wt, a.n_ev = n_use, a.freqs = d_freqs, a.n_f = n_f, a.fdots = d_fdots;
     a.n_trials = n_trials, a.nbin = nbin, a.warps = W, a.ev_per_split = ev_per_split;
     a.scratch = b_scratch.as<double>(), a.unit_weight = unit_weight;
     wfold_fn_t fn = pick_wfold(cell, R, U, has_fd, mode);
@@ -620,7 +679,7 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
 
 extern "C" {
 
-int hx_wfold_last_kernel_ms(double *ms, int *cell_kind) {
+int hx_wfold_last_kernel_ms(double *ms, int *cell_kind, int64_t *n_events_folded) {
     if (!ms || hx::g_wlast_device < 0) {
         hx::set_error("hx_wfold_last_kernel_ms: no weighted fold kernel has been launched");
         return HX_ERR_ARG;
@@ -631,6 +690,7 @@ int hx_wfold_last_kernel_ms(double *ms, int *cell_kind) {
     HX_CUDA_TRY(cudaEventElapsedTime(&f, hx::g_wev0[d], hx::g_wev1[d]));
     *ms = f;
     if (cell_kind) *cell_kind = hx::g_wlast_cell;
+    if (n_events_folded) *n_events_folded = hx::g_wlast_n_used;
     return HX_OK;
 }
 
@@ -638,7 +698,7 @@ int hx_wfold_set_tuning(int trials_per_thread, int events_per_group, int warps_p
     hx::g_wfold_R = (trials_per_thread == 1 || trials_per_thread == 2 || trials_per_thread == 4) ? trials_per_thread : 0;
     hx::g_wfold_U = (events_per_group == 2 || events_per_group == 4) ? events_per_group : 0;
     hx::g_wfold_W = (warps_per_cta >= 1 && warps_per_cta <= 16) ? warps_per_cta : 0;
-    hx::g_wfold_force_generic = force_generic & 3;  // bit 0: never WMODE_FAST; bit 1: fp64 cells even for integers
+    hx::g_wfold_force_generic = force_generic & 7;  // bit 0: never WMODE_FAST; bit 1: fp64 cells even for integers; bit 2: keep zero weights
     return HX_OK;
 }
 

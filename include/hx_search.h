@@ -103,8 +103,9 @@ int hx_wfold_search_dev(const double *d_times, const double *d_weights, double u
                         const double *gti, int64_t n_gti, double start_time, double stop_time, double *d_stats,
                         double *d_profiles, void *stream);
 /* Device time of the wfold_kernel launches of the most recent hx_wfold_search* call and the histogram cell type it
- * chose: 0 = fp64 cells (arbitrary weights), 1 = uint32 cells (integer weights), 2 = uint32 cells (no weight array). */
-int hx_wfold_last_kernel_ms(double *ms, int *cell_kind);
+ * chose: 0 = fp64 cells (arbitrary weights), 1 = uint32 cells (integer weights), 2 = uint32 cells (no weight array);
+ * n_events_folded = events actually streamed (zero-weight entries are dropped when they are more than a quarter). */
+int hx_wfold_last_kernel_ms(double *ms, int *cell_kind, int64_t *n_events_folded);
 
 /* ---- K2 + K3: one centre step of the `--fast` quasi-fast-folding search ------------------
  * Replaces hendrics/efsearch.py:876-925 (search_with_qffa_step) = _fast_phase* (:854-873) +
@@ -184,6 +185,8 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  *   kinds 7..10: the kind-4 mix with 2, 4, 6, 8 of every 8 floors taken through F2I (XU) instead of the magic add
  *   kinds 11, 12: K1's (f, fdot) loop at K1's occupancy (12 warps/SM) with the fdot term computed per thread (11) or
  *           read from a per-CTA shared-memory tile (12) -> units/s   (experiments recorded in DESIGN.md)
+ *   kinds 13, 14: K1's f-only loop with the events broadcast from shared memory (13) or __constant__ memory (14)
+ *   kinds 15, 16: as 11, 12 with 4 trials per thread at 6 warps/SM
  * Runs on `device`, blocks, returns the best of `reps` timings.
  */
 int hx_microbench(int kind, int reps, double *ops_per_s, int device);
@@ -199,7 +202,8 @@ int hx_qffa_last_kernel_ms(double *ms, int64_t *launches);
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);
-/* force_generic bit 0: never use the pre-scaled fast bin path; bit 1: fp64 cells even for integer weights */
+/* force_generic bit 0: never use the pre-scaled fast bin path; bit 1: fp64 cells even for integer weights;
+ * bit 2: never drop zero-weight entries */
 int hx_wfold_set_tuning(int trials_per_thread, int events_per_group, int warps_per_cta, int force_generic);
 int hx_fold_set_packing(int mode); /* 0: never pack counters, 1: whenever possible, other: automatic */
 

@@ -272,3 +272,42 @@ def test_negative_phases_take_the_generic_bin_path():
         np.testing.assert_allclose(stats, _oracle_stats(ref_p, 2), rtol=RTOL_STAT)
         _, pi = fold_profiles_weighted(ts, freqs, [0.0, -2e-5], nbin=nbin, nharm=2, weights=np.ones(ts.size))
         assert np.array_equal(pi, _oracle_profiles(ts, freqs, [0.0, -2e-5], nbin, 1))
+
+
+@pytest.mark.parametrize("kind", ["counts", "float"])
+def test_sparse_light_curve_drops_empty_bins(kind):
+    """A light curve at fine time resolution is mostly zeros: they are dropped before the fold (adding a zero weight
+    changes nothing) and the profiles stay identical to the oracle's, which folds every bin like upstream."""
+    from hendrics_b200 import _cabi
+    from hendrics_b200.search import fold_profiles_weighted
+
+    ph = O.simulate_events(20000, 2000.0, seed=17)
+    edges = np.arange(0.0, 2000.0 + 1e-9, 2e-3)  # 10^6 bins, 2 % occupied
+    counts = np.histogram(ph, bins=edges)[0].astype(np.float64)
+    t = (edges[:-1] + edges[1:]) / 2
+    w = counts if kind == "counts" else counts * 0.37
+    freqs = 9.85 + 0.002 * np.arange(40)
+    lib = _cabi.lib()
+    try:
+        stats, prof = fold_profiles_weighted(t, freqs, [0.0, 1e-7], nbin=32, nharm=2, weights=w)
+        ms, cell, n_used = _cabi.wfold_last_kernel()
+        assert n_used == np.count_nonzero(w) < 0.03 * t.size and cell == (1 if kind == "counts" else 0)
+        lib.hx_wfold_set_tuning(0, 0, 0, 4)  # keep the zeros
+        stats_all, prof_all = fold_profiles_weighted(t, freqs, [0.0, 1e-7], nbin=32, nharm=2, weights=w)
+        assert _cabi.wfold_last_kernel()[2] == t.size
+    finally:
+        lib.hx_wfold_set_tuning(0, 0, 0, 0)
+    if kind == "counts":
+        assert np.array_equal(prof, prof_all) and np.array_equal(stats, stats_all)
+    else:  # the split of the event list over CTAs differs: fp64 partial sums combine in another order
+        np.testing.assert_allclose(prof, prof_all, rtol=1e-13)
+        np.testing.assert_allclose(stats, stats_all, rtol=1e-11)
+    ref_p = _oracle_profiles(t, freqs[:6], [0.0, 1e-7], 32, w)
+    if kind == "counts":
+        assert np.array_equal(prof[:, :6], ref_p)
+    else:
+        np.testing.assert_allclose(prof[:, :6], ref_p, rtol=1e-12)
+    np.testing.assert_allclose(stats[:, :6], _oracle_stats(ref_p, 2), rtol=RTOL_STAT)
+    # all-zero weights: empty profiles, like upstream (0/0 statistics)
+    _, p0 = fold_profiles_weighted(t[:1000], freqs[:3], [0.0], nbin=16, nharm=0, weights=np.zeros(1000))
+    assert not p0.any()

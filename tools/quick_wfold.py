@@ -48,3 +48,18 @@ if __name__ == "__main__":
     run(1_000_000, 2_000, 8, 64, 2)
     run(1_000_000, 20_000, 1, 100, 2)
     run(100_000, 100_000, 1, 64, 0, weighted=False, n_gti=100)
+    # sparse light curve: 1e7 bins, 1 % occupied
+    rng = np.random.default_rng(1)
+    n = 10_000_000
+    t = (np.arange(n) + 0.5) * 1e-2
+    w = (rng.random(n) < 0.01).astype(np.float64)
+    ts, wd = torch.from_numpy(t).cuda(), torch.from_numpy(w).cuda()
+    f = torch.from_numpy(9.0 + 5e-6 * np.arange(20000)).cuda(); fd = torch.zeros(1, dtype=torch.float64).cuda()
+    for keep in (0, 4):
+        _cabi.lib().hx_wfold_set_tuning(0, 0, 0, keep)
+        wfold_stats_device(ts, wd, 1.0, f, fd, 64, 2)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        wfold_stats_device(ts, wd, 1.0, f, fd, 64, 2)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(f"sparse light curve 1e7 bins x 2e4 f, 1% occupied, keep_zeros={keep != 0}: {dt*1e3:8.2f} ms, folded {_cabi.wfold_last_kernel()[2]} events", flush=True)
+    _cabi.lib().hx_wfold_set_tuning(0, 0, 0, 0)
