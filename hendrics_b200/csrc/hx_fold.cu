@@ -150,6 +150,16 @@ struct EvGroup {
             t[u] = v.x, t[u + 1] = v.y;
         }
     }
+    // M2T: the fdot terms fl(fl(t*t) * fdH) of the stage were computed once per CTA into a second tile
+    __device__ __forceinline__ void load_m2(const unsigned char *mp, int e) {
+        if (HAS_FD) {
+#pragma unroll
+            for (int u = 0; u < UE; u += 2) {
+                double2 v = *reinterpret_cast<const double2 *>(mp + (size_t)(e + u) * 8);
+                m2[u] = v.x, m2[u + 1] = v.y;
+            }
+        }
+    }
     // fdH_row: the thread's fdot constant when all its trials share it (ROWFD), else unused
     __device__ __forceinline__ void squares(double fdH_row = 0.0) {
         if (HAS_FD) {
@@ -173,9 +183,14 @@ struct GroupSize {
 
 // ROWFD: the R trials of a thread lie in the same fdot row (trial blocks are laid out row by row, rows
 // padded to a multiple of 32*R), so the fdot term is one DMUL per event and thread instead of per trial.
-template <int R, bool HAS_FD, int MODE, bool ROWFD>
+// M2T (with ROWFD, CTAs aligned on fdot rows): the fdot term of every event of a stage is computed ONCE per CTA into a
+// second shared-memory tile and broadcast like the times -- 3 FP64 ops per event*trial (DMUL, DADD, DADD.RM) instead
+// of 3 + 2/R, for one more shared-memory wavefront per event and warp.  Every warp computes the (identical) tile
+// itself right after the stage lands, so no block barrier is needed: concurrent writers store the same values.
+template <int R, bool HAS_FD, int MODE, bool ROWFD, bool M2T = false>
 __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     static_assert(!ROWFD || HAS_FD, "ROWFD only makes sense with fdot");
+    static_assert(!M2T || (ROWFD && MODE != MODE_EXACT), "M2T needs fdot rows and a fp64 parity mode");
     constexpr bool POW2 = MODE == MODE_POW2 || MODE == MODE_PACKED;
     constexpr bool PACKED = MODE == MODE_PACKED;
     constexpr bool EXACT = MODE == MODE_EXACT;
@@ -190,6 +205,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     const int TILE_EV = a.tile_ev;
     const uint32_t TILE_BYTES = (uint32_t)(TILE_EV + TILE_PAD) * 8u;
     int *done = reinterpret_cast<int *>(smem + 16);  // [2] warps that finished the stage
+    const uint32_t m2_off = a.tile_off + 2u * TILE_BYTES;  // M2T: two stages of fdot terms behind the two stages of times
 
     if (POW2 && (hist & (blk - 1)) != 0) {  // host/device layout disagreement: refuse to compute
         if (tid == 0) atomicExch(a.errflag, 1);
@@ -241,6 +257,10 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
         for (int r = 0; r < R; r++)
             if (valid[r]) fdH_row = fdH[r];
+    }
+    if (M2T) {  // CTA-uniform (rows are padded to whole CTAs): also right for lanes without a valid trial
+        const long long ifd_cta = min((a.tb0 + (long long)blockIdx.x * a.warps) / a.n_tb_row, a.n_trials / a.n_f - 1);
+        fdH_row = __dmul_rn(__dmul_rn(0.5, a.fdots[ifd_cta]), a.scale);
     }
 
     // event range of this CTA
@@ -307,6 +327,14 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
         const int cnt = (int)min((long long)TILE_EV, e1 - (e0 + (long long)it * TILE_EV));
         const unsigned char *tp = smem + a.tile_off + (uint32_t)buf * TILE_BYTES;
+        unsigned char *mp = smem + m2_off + (uint32_t)buf * TILE_BYTES;
+        if (M2T) {
+            for (int q = lane; q < cnt; q += 32) {
+                const double tq = *reinterpret_cast<const double *>(tp + (size_t)q * 8);
+                *reinterpret_cast<double *>(mp + (size_t)q * 8) = __dmul_rn(__dmul_rn(tq, tq), fdH_row);
+            }
+            __syncwarp();
+        }
 
         int e = 0;
         EvGroup<HAS_FD, UE, EXACT> cur, nxt;
@@ -325,7 +353,8 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         if (ngroups > 0) {
             cur.load(tp, 0);
             nxt.load(tp, UE);
-            cur.squares(fdH_row);
+            if (M2T) cur.load_m2(mp, 0), nxt.load_m2(mp, UE);
+            else cur.squares(fdH_row);
 #pragma unroll
             for (int i = 0; i < UE * R; i++) {
                 uint32_t inc;
@@ -335,9 +364,13 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
             for (int g = 0; g < ngroups; g++) {
                 // group g+1 (garbage past the last group: computed, never issued)
 #pragma unroll
-                for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
+                for (int u = 0; u < UE; u++) {
+                    cur.t[u] = nxt.t[u];
+                    if (M2T) cur.m2[u] = nxt.m2[u];
+                }
                 nxt.load(tp, (g + 2) * UE);  // may read the pad after the stage; never used past cnt
-                cur.squares(fdH_row);
+                if (M2T) nxt.load_m2(mp, (g + 2) * UE);
+                else cur.squares(fdH_row);
 #pragma unroll
                 for (int i = 0; i < UE * R; i++) {
                     uint32_t inc;
@@ -356,9 +389,11 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         }
         } else {
         cur.load(tp, 0);
+        if (M2T) cur.load_m2(mp, 0);
         for (; e + UE <= cnt; e += UE) {
             nxt.load(tp, e + UE);  // may read the pad after the stage; never used past cnt
-            cur.squares(fdH_row);
+            if (M2T) nxt.load_m2(mp, e + UE);
+            else cur.squares(fdH_row);
 #pragma unroll
             for (int u = 0; u < UE; u++) {
 #pragma unroll
@@ -372,7 +407,10 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < UE; u++) cur.t[u] = nxt.t[u];
+            for (int u = 0; u < UE; u++) {
+                cur.t[u] = nxt.t[u];
+                if (M2T) cur.m2[u] = nxt.m2[u];
+            }
         }
         }
         for (; e < cnt; e++) {  // ragged end of the last stage
@@ -500,16 +538,19 @@ struct FoldPlan {
     uint32_t hist_off, tile_off, smem_bytes;
 };
 
-static uint32_t tile_region_bytes(int tile_ev, int nbin) {
-    return std::max<uint32_t>(2u * (uint32_t)(tile_ev + TILE_PAD) * 8u, (uint32_t)nbin * 16u);
+// two stages of times (+ two stages of fdot terms with M2T); the fused epilogue reuses the region for its tables
+static uint32_t tile_region_bytes(int tile_ev, int nbin, bool m2t) {
+    return std::max<uint32_t>((m2t ? 4u : 2u) * (uint32_t)(tile_ev + TILE_PAD) * 8u, (uint32_t)nbin * 16u);
 }
 
-static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, int regs, FoldPlan *p) {
+static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, int regs, bool m2t, FoldPlan *p) {
     const bool pow2 = mode == MODE_POW2 || mode == MODE_PACKED;
     const uint32_t blk = (uint32_t)nbin * (mode == MODE_PACKED ? 64u : 128u);
     const uint32_t hist_bytes = (uint32_t)W * R * blk;
     uint32_t hist_off, tile_off;
-    int tile_ev = TILE_EV_MAX;
+    int tile_ev = m2t ? TILE_EV_MAX / 2 : TILE_EV_MAX;  // M2T stages hold two arrays; small stages keep 3 CTAs per SM at nbin = 128
+    if (m2t)
+        if (const char *e = getenv("HX_FOLD_M2T_TILE")) tile_ev = std::max(64, std::min(TILE_EV_MAX, atoi(e) / 64 * 64));  // tuning hook
     if (pow2) {
         uint32_t abs0 = di.dyn_smem_base + SMEM_HDR;
         uint32_t hist_abs = (abs0 + blk - 1) / blk * blk;
@@ -517,8 +558,8 @@ static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, 
         const uint32_t gap = hist_off - SMEM_HDR;
         // largest stage that fits in the alignment gap in front of the histograms, if any does
         int fit = 0;
-        for (int t = TILE_EV_MAX; t >= 256; t -= 64)
-            if (tile_region_bytes(t, nbin) <= gap) {
+        for (int t = TILE_EV_MAX; t >= (m2t ? 128 : 256); t -= 64)
+            if (tile_region_bytes(t, nbin, m2t) <= gap) {
                 fit = t;
                 break;
             }
@@ -532,7 +573,7 @@ static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, 
         hist_off = SMEM_HDR;
         tile_off = hist_off + hist_bytes;
     }
-    uint32_t total = std::max(hist_off + hist_bytes, tile_off + tile_region_bytes(tile_ev, nbin));
+    uint32_t total = std::max(hist_off + hist_bytes, tile_off + tile_region_bytes(tile_ev, nbin, m2t));
     if (total > (uint32_t)di.smem_optin) return false;
     int k_smem = di.smem_per_sm / (int)(total + di.reserved_smem);
     const int regs_alloc = (regs + 7) / 8 * 8;                 // register allocation granularity
@@ -545,24 +586,33 @@ static bool plan_layout(const DeviceInfo &di, int nbin, int R, int W, int mode, 
 }
 
 typedef void (*fold_fn_t)(const FoldArgs);
-template <int R, bool HAS_FD, bool ROWFD>
+template <int R, bool HAS_FD, bool ROWFD, bool M2T>
 static fold_fn_t pick_fold_M(int mode) {
-    return mode == MODE_PACKED ? fold_kernel<R, HAS_FD, MODE_PACKED, ROWFD>
-           : mode == MODE_POW2 ? fold_kernel<R, HAS_FD, MODE_POW2, ROWFD>
-           : mode == MODE_EXACT ? fold_kernel<R, HAS_FD, MODE_EXACT, ROWFD>
-                                : fold_kernel<R, HAS_FD, MODE_GENERIC, ROWFD>;
+    if constexpr (M2T) {
+        return mode == MODE_PACKED ? fold_kernel<R, HAS_FD, MODE_PACKED, ROWFD, true>
+               : mode == MODE_POW2 ? fold_kernel<R, HAS_FD, MODE_POW2, ROWFD, true>
+                                   : fold_kernel<R, HAS_FD, MODE_GENERIC, ROWFD, true>;
+    } else {
+        return mode == MODE_PACKED ? fold_kernel<R, HAS_FD, MODE_PACKED, ROWFD>
+               : mode == MODE_POW2 ? fold_kernel<R, HAS_FD, MODE_POW2, ROWFD>
+               : mode == MODE_EXACT ? fold_kernel<R, HAS_FD, MODE_EXACT, ROWFD>
+                                    : fold_kernel<R, HAS_FD, MODE_GENERIC, ROWFD>;
+    }
 }
 template <int R>
-static fold_fn_t pick_fold_R(bool has_fd, int mode, bool rowfd) {
-    if (!has_fd) return pick_fold_M<R, false, false>(mode);
-    return rowfd ? pick_fold_M<R, true, true>(mode) : pick_fold_M<R, true, false>(mode);
+static fold_fn_t pick_fold_R(bool has_fd, int mode, bool rowfd, bool m2t) {
+    if (!has_fd) return pick_fold_M<R, false, false, false>(mode);
+    if constexpr (R == 2 || R == 4) {
+        if (rowfd && m2t && mode != MODE_EXACT) return pick_fold_M<R, true, true, true>(mode);
+    }
+    return rowfd ? pick_fold_M<R, true, true, false>(mode) : pick_fold_M<R, true, false, false>(mode);
 }
-static fold_fn_t pick_fold(int R, bool has_fd, int mode, bool rowfd) {
+static fold_fn_t pick_fold(int R, bool has_fd, int mode, bool rowfd, bool m2t = false) {
     switch (R) {
-        case 1: return pick_fold_R<1>(has_fd, mode, false);  // one trial per thread: nothing to share
-        case 2: return pick_fold_R<2>(has_fd, mode, rowfd);
-        case 4: return pick_fold_R<4>(has_fd, mode, rowfd);
-        default: return pick_fold_R<8>(has_fd, mode, rowfd);
+        case 1: return pick_fold_R<1>(has_fd, mode, false, false);  // one trial per thread: nothing to share
+        case 2: return pick_fold_R<2>(has_fd, mode, rowfd, m2t);
+        case 4: return pick_fold_R<4>(has_fd, mode, rowfd, m2t);
+        default: return pick_fold_R<8>(has_fd, mode, rowfd, false);
     }
 }
 
@@ -575,6 +625,7 @@ static long long g_last_grid = 0, g_last_block = 0, g_last_smem = 0;
 static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
 static int g_fold_pack_override = -1;  // -1 auto, 0 never, 1 whenever possible
+static int g_fold_m2t = 1;             // per-CTA fdot-term tile (M2T) when applicable; HX_FOLD_M2T=0 disables it
 
 // min/max of the event times, trial frequencies and fdots (device arrays): out = [tmin,tmax, fmin,fmax, fdmin,fdmax];
 // fails with HX_ERR_ARG when any of them is not finite.  Synchronizes `st`.
@@ -679,10 +730,15 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     else R = 1, W_pref = 4;
     if (g_fold_R_override) R = g_fold_R_override;
     if (g_fold_W_override) W_pref = g_fold_W_override;
+    bool m2t_on = g_fold_m2t != 0;
+    if (const char *e = getenv("HX_FOLD_M2T")) m2t_on = atoi(e) != 0;  // tuning hook
+    // M2T pays when the fdot term is shared by few trials per thread (it removes 2/R FP64 ops per unit)
+    // (measured on B200: +10 % at R = 2 -- C3 3.21e12 -> 3.54e12 --, -2 % at R = 4 where only 0.5 op per unit is saved)
+    auto use_m2t = [&](int r) { return m2t_on && has_fd && r == 2 && n_f >= 32LL * r && mode != MODE_EXACT; };
     auto kernel_regs = [&](int r, int *out) -> int {
         cudaFuncAttributes fa;
         const bool rf = has_fd && r >= 2 && n_f >= 32LL * r && mode != MODE_EXACT;
-        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, mode, rf))));
+        HX_CUDA_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(pick_fold(r, has_fd, mode, rf, use_m2t(r)))));
         *out = fa.numRegs;
         return HX_OK;
     };
@@ -690,7 +746,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     if ((rc = kernel_regs(R, &regs)) != HX_OK) return rc;
     FoldPlan best{};
     int best_res = -1;
-    if (plan_layout(di, nbin, R, W_pref, mode, regs, &best)) best_res = best.ctas_per_sm * W_pref;
+    if (plan_layout(di, nbin, R, W_pref, mode, regs, use_m2t(R), &best)) best_res = best.ctas_per_sm * W_pref;
     for (int pass = 0; pass < 2 && best_res < 0; pass++) {
         if (pass == 1) {  // very large nbin: one trial per thread
             if (R == 1) break;
@@ -699,7 +755,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         }
         for (int W = 1; W <= 16; W++) {
             FoldPlan p;
-            if (!plan_layout(di, nbin, R, W, mode, regs, &p)) continue;
+            if (!plan_layout(di, nbin, R, W, mode, regs, use_m2t(R), &p)) continue;
             int res = p.ctas_per_sm * W;
             if (res > best_res) best = p, best_res = res;
         }
@@ -710,9 +766,9 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     }
     // ROWFD: threads with R >= 2 trials take them from one fdot row (rows padded to 32*R frequencies)
     const bool rowfd = has_fd && R >= 2 && n_f >= 32LL * R && mode != MODE_EXACT;
-    const long long n_tb_row = (n_f + 32LL * R - 1) / (32LL * R);
-    const long long n_fp = rowfd ? n_tb_row * 32LL * R : 0;  // padded row length in kernel order
-    const long long n_tb = rowfd ? n_tb_row * n_fd : (n_trials + 32LL * R - 1) / (32LL * R);  // 32*R-trial blocks
+    const bool m2t = rowfd && use_m2t(R);
+    long long n_tb_row = (n_f + 32LL * R - 1) / (32LL * R);
+    long long n_tb = rowfd ? n_tb_row * n_fd : (n_trials + 32LL * R - 1) / (32LL * R);  // 32*R-trial blocks
     int W = best.W;
     // few trials: shrink CTAs so that every SM gets one, then split the events across CTAs
     {
@@ -720,9 +776,14 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         if (want < W) {
             int Wn = (int)std::max<long long>(1, want);
             FoldPlan p;
-            if (plan_layout(di, nbin, R, Wn, mode, regs, &p)) best = p, W = Wn;
+            if (plan_layout(di, nbin, R, Wn, mode, regs, m2t, &p)) best = p, W = Wn;
         }
     }
+    if (m2t) {  // whole CTAs per fdot row: the fdot-term tile of a CTA is for ONE fdot
+        n_tb_row = (n_tb_row + W - 1) / W * W;
+        n_tb = n_tb_row * n_fd;
+    }
+    const long long n_fp = rowfd ? n_tb_row * 32LL * R : 0;  // padded row length in kernel order
     // trial batching bounds the global scratch of the non-fused path (1 GiB)
     const size_t scratch_per_tb = (size_t)R * nbin * 32 * sizeof(uint32_t);
     size_t scratch_cap = (size_t)1 << 30;
@@ -791,7 +852,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     a.errflag = d_err;
 
     a.n_tb_row = n_tb_row;
-    fold_fn_t fn = pick_fold(R, has_fd, mode, rowfd);
+    fold_fn_t fn = pick_fold(R, has_fd, mode, rowfd, m2t);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem_bytes));
     if (!g_ev_ok[device]) {
         HX_CUDA_TRY(cudaEventCreate(&g_ev0[device]));
