@@ -690,7 +690,12 @@ def main():
         mix_ceiling = _cabi.microbench(4 if has_fd else 5, reps=3, device=local_rank)
         alg_ops = algorithmic_ops_per_evtr(has_fd) * units_local
         achieved = alg_ops / (kern_avg_ms * 1e-3)
-        exec_ops = (4.0 if has_fd else 2.0) * units_local / (kern_avg_ms * 1e-3)
+        shape = _cabi.fold_last_kernel_shape()  # instantiation of the timed launches
+        exec_ops = shape["fp64_per_unit"] * units_local / (kern_avg_ms * 1e-3)
+        # shared-memory data pipe: 1 wavefront/clk/SM; K1 needs one per increment (ATOMS) plus the broadcast event loads
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        smem_peak_wf = n_sm * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        smem_wf = shape["smem_wavefronts_per_unit"] * units_local / 32.0 / (kern_avg_ms * 1e-3)
         traffic = None
         prof = os.path.join(ROOT, "profiles", f"fold_{wl}_ncu_summary.json")
         if os.path.exists(prof):
@@ -705,7 +710,11 @@ def main():
             "frac": achieved / peak_ops, "traffic": traffic,
             "kernel": "hx::fold_kernel", "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
             "algorithmic_fp64_ops_per_event_trial": algorithmic_ops_per_evtr(has_fd),
+            "executed_fp64_ops_per_event_trial": shape["fp64_per_unit"],
             "executed_fp64_frac": exec_ops / peak_ops,
+            "smem_pipe_frac_model": smem_wf / smem_peak_wf,
+            "smem_wavefronts_per_event_trial_model": shape["smem_wavefronts_per_unit"],
+            "kernel_variant": {k: shape[k] for k in ("R", "mode", "rowfd", "m2t")},
             "mix_ceiling_units_per_s": mix_ceiling,
             "frac_of_mix_ceiling": units_local / (kern_avg_ms * 1e-3) / mix_ceiling,
             "peak_source": "measured in this process: hx_microbench kind 1 (DMUL+DADD issue rate, non-FMA op/s); "

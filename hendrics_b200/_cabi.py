@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libhxsearch.so")
+# HX_LIB_PATH: development hook (tools/variant_bench.py loads experimental builds of the same ABI)
+LIB_PATH = os.environ.get("HX_LIB_PATH") or os.path.join(_PKG_DIR, "libhxsearch.so")
 
 HX_OK = 0
 HX_ERR_ARG, HX_ERR_CUDA, HX_ERR_NOMEM, HX_ERR_RANGE, HX_ERR_INTERNAL = -1, -2, -3, -4, -5
@@ -50,6 +51,7 @@ SIGNATURES = {
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
     "hx_microbench": (_int, [_int, _int, _c_dp, _int]),
     "hx_fold_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
+    "hx_fold_last_kernel_shape": (_int, [ctypes.POINTER(_int)] * 4 + [_c_dp, _c_dp]),
     "hx_qffa_last_kernel_ms": (_int, [_c_dp, _c_i64p]),
     "hx_fold_set_tuning": (_int, [_int, _int]),
     "hx_qffa_set_tuning": (_int, [_int]),
@@ -132,6 +134,15 @@ def fold_last_kernel():
     ms, g, b, s = _dbl(0.0), _i64(0), _i64(0), _i64(0)
     check(lib().hx_fold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
     return ms.value, g.value, b.value, s.value
+
+
+def fold_last_kernel_shape():
+    """dict(R, mode, rowfd, m2t, fp64_per_unit, smem_wavefronts_per_unit) of the last K1 launch."""
+    iv = [_int() for _ in range(4)]
+    a, b = _dbl(), _dbl()
+    check(lib().hx_fold_last_kernel_shape(*[ctypes.byref(x) for x in iv], ctypes.byref(a), ctypes.byref(b)))
+    return {"R": iv[0].value, "mode": iv[1].value, "rowfd": iv[2].value, "m2t": iv[3].value,
+            "fp64_per_unit": a.value, "smem_wavefronts_per_unit": b.value}
 
 
 def wfold_last_kernel():

@@ -621,6 +621,7 @@ static cudaEvent_t g_ev0[64], g_ev1[64];
 static bool g_ev_ok[64] = {false};
 static int g_last_timed_device = -1;
 static long long g_last_grid = 0, g_last_block = 0, g_last_smem = 0;
+static int g_last_R = 0, g_last_mode = 0, g_last_rowfd = 0, g_last_m2t = 0, g_last_has_fd = 0;
 
 static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
@@ -724,7 +725,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     const int foot = mode == MODE_PACKED ? nbin / 2 : nbin;  // histogram words per trial
     int R, W_pref;
     if (foot <= 16) R = has_fd ? 8 : 4, W_pref = has_fd ? 2 : 8;
-    else if (foot <= 32) R = 4, W_pref = 4;
+    else if (foot <= 32) R = has_fd ? 2 : 4, W_pref = 4;  // with fdot: R = 2 takes the fdot-term tile (M2T), +3 % (profiles/r01_sweep_r3.txt)
     else if (foot <= 64) R = 2, W_pref = 4;
     else if (foot <= 128) R = 1, W_pref = 12;
     else R = 1, W_pref = 4;
@@ -882,6 +883,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     }
     g_last_timed_device = device;
     g_last_grid = total_ctas, g_last_block = W * 32, g_last_smem = best.smem_bytes;
+    g_last_R = R, g_last_mode = mode, g_last_rowfd = rowfd, g_last_m2t = m2t, g_last_has_fd = has_fd;
     int herr = 0;
     HX_CUDA_TRY(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     HX_CUDA_TRY(cudaStreamSynchronize(st));
@@ -909,6 +911,30 @@ int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *s
     if (grid) *grid = hx::g_last_grid;
     if (block) *block = hx::g_last_block;
     if (smem_bytes) *smem_bytes = hx::g_last_smem;
+    return HX_OK;
+}
+
+int hx_fold_last_kernel_shape(int *R, int *mode, int *rowfd, int *m2t, double *fp64_per_unit,
+                              double *smem_wavefronts_per_unit) {
+    if (hx::g_last_timed_device < 0) {
+        hx::set_error("hx_fold_last_kernel_shape: no fold kernel has been launched");
+        return HX_ERR_ARG;
+    }
+    const int r = hx::g_last_R;
+    if (R) *R = r;
+    if (mode) *mode = hx::g_last_mode;
+    if (rowfd) *rowfd = hx::g_last_rowfd;
+    if (m2t) *m2t = hx::g_last_m2t;
+    const bool fast = hx::g_last_mode == hx::MODE_POW2 || hx::g_last_mode == hx::MODE_PACKED;
+    if (fp64_per_unit) {
+        // f only: DMUL + DADD.RM.  With fdot: + DADD, and the fdot term fl(fl(t*t)*fdH): from the per-CTA tile (m2t, 0 per
+        // unit), 2 DMUL per event and thread (rowfd) or 1 DMUL per event and thread + 1 per unit.
+        double n = 2.0;
+        if (hx::g_last_has_fd) n = hx::g_last_m2t ? 3.0 : hx::g_last_rowfd ? 3.0 + 2.0 / r : 4.0 + 1.0 / r;
+        *fp64_per_unit = fast ? n : -1.0;
+    }
+    if (smem_wavefronts_per_unit)  // one ATOMS per unit; a broadcast fp64 costs one wavefront per event and warp (LDS.128 = 2 events)
+        *smem_wavefronts_per_unit = 1.0 + (hx::g_last_m2t ? 2.0 : 1.0) / r;
     return HX_OK;
 }
 

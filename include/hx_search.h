@@ -195,6 +195,14 @@ int hx_microbench(int kind, int reps, double *ops_per_s, int device);
  * fold_kernel launch of this process. */
 int hx_fold_last_kernel_ms(double *ms, int64_t *grid, int64_t *block, int64_t *smem_bytes);
 
+/* Instantiation of that launch: trials per thread R, histogram mode (0 generic, 1 power-of-two, 2 packed, 3 exact
+ * phase), whether the R trials of a thread share their fdot (rowfd) and whether the fdot term comes from the per-CTA
+ * tile (m2t); *fp64_per_unit = FP64 instructions the inner loop issues per event*trial (-1 for the generic / exact
+ * modes, whose count depends on the data), *smem_wavefronts_per_unit = shared-memory data-pipe wavefronts per
+ * event*trial and warp (one per increment + the broadcast event loads).  bench.py's executed-work figures. */
+int hx_fold_last_kernel_shape(int *R, int *mode, int *rowfd, int *m2t, double *fp64_per_unit,
+                              double *smem_wavefronts_per_unit);
+
 /* Summed device time of the K2 (qffa_hist_kernel) launches of the most recent hx_qffa_search* call
  * and their number. */
 int hx_qffa_last_kernel_ms(double *ms, int64_t *launches);
