@@ -49,6 +49,12 @@ SIGNATURES = {
     "hx_zn_unbinned_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
+    "hx_hist1d_dev": (_int, [_vp, _i64, _dbl, _dbl, _i64, _vp, _vp]),
+    "hx_rebin_u32_dev": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "hx_ffa": (_int, [_c_u32p, _i64, _i64, _int, _c_dp, _c_dp, _i64, _int]),
+    "hx_ffa_dev": (_int, [_vp, _i64, _i64, _int, _c_dp, _vp, _i64, _vp]),
+    "hx_ffa_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
+    "hx_ffa_set_tuning": (_int, [_int]),
     "hx_microbench": (_int, [_int, _int, _c_dp, _int]),
     "hx_fold_last_kernel_ms": (_int, [_c_dp, _c_i64p, _c_i64p, _c_i64p]),
     "hx_fold_last_kernel_shape": (_int, [ctypes.POINTER(_int)] * 4 + [_c_dp, _c_dp]),
@@ -143,6 +149,14 @@ def fold_last_kernel_shape():
     check(lib().hx_fold_last_kernel_shape(*[ctypes.byref(x) for x in iv], ctypes.byref(a), ctypes.byref(b)))
     return {"R": iv[0].value, "mode": iv[1].value, "rowfd": iv[2].value, "m2t": iv[3].value,
             "fp64_per_unit": a.value, "smem_wavefronts_per_unit": b.value}
+
+
+def ffa_last_kernel():
+    """(ms, passes over HBM, folding steps, steps fused per pass) of the last hx_ffa* call."""
+    ms = _dbl()
+    v = [_i64() for _ in range(3)]
+    check(lib().hx_ffa_last_kernel_ms(ctypes.byref(ms), *[ctypes.byref(x) for x in v]))
+    return ms.value, v[0].value, v[1].value, v[2].value
 
 
 def wfold_last_kernel():

@@ -38,6 +38,7 @@ from .base import (
     z2_n_detection_level,
 )
 from .io import HEN_FILE_EXTENSION, EFPeriodogram, get_file_type, load_folding, save_folding
+from .ffa import ffa_search
 from .search import epoch_folding_search, z_n_search
 
 log = logging.getLogger("hendrics_b200")
@@ -45,7 +46,7 @@ log = logging.getLogger("hendrics_b200")
 __all__ = [
     "folding_search", "search_with_qffa", "search_with_qffa_step", "check_phase_error_after_casting_to_double",
     "dyn_folding_search", "transient_search", "TransientResults", "analyze_qffa_results", "main_efsearch", "main_zsearch", "z_n_search",
-    "epoch_folding_search", "qffa_centres",
+    "epoch_folding_search", "qffa_centres", "search_with_ffa",
 ]
 
 
@@ -435,6 +436,34 @@ def search_with_qffa(
 # ---------------------------------------------------------------------------------------------
 # transient search (widening: SURVEY.md section 8f, rank 4)
 # ---------------------------------------------------------------------------------------------
+def search_with_ffa(times, f0, f1, nbin=16, n=1, t0=None, t1=None):
+    """Fast-folding-algorithm search: mirror of ``hendrics/efsearch.py:1092-1138``.
+
+    The light curve (bin time = 1/f1/nbin) is built on the GPU by ``hx_hist1d_dev`` and never leaves it;
+    ``ffa_search`` folds it (``hx_ffa_dev``).  Returns ``(frequencies, stats, None, length)`` like the reference;
+    ``n`` is accepted and ignored like there (the reference's ``ffa_search`` always computes Z^2_2).
+    """
+    import torch
+
+    times = np.asarray(times)
+    if t0 is None:
+        t0 = times[0]
+    if t1 is None:
+        t1 = times[-1]
+    length = np.asarray(t1 - t0).astype(np.double)
+    p0 = 1 / f1
+    p1 = 1 / f0
+    dt = p0 / nbin
+    bins = int(np.rint(length / dt))
+    x = _to_device((times - t0).astype(np.double))
+    counts = torch.empty(bins, dtype=torch.int32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().hx_hist1d_dev(x.data_ptr(), x.numel(), 0.0, float(length), bins, counts.data_ptr(), stream))
+    bin_periods, stats = ffa_search(counts, dt, p0, p1)
+    return 1 / bin_periods, stats, None, length
+
+
 class TransientResults:
     """Same fields as hendrics/efsearch.py:488-496."""
 
@@ -755,8 +784,7 @@ def _common_main(args, func):
 
     if func != z_n_search and args.fast:
         raise ValueError("The fast option is only available for z searches")
-    for flag, name in [(args.ffa, "--ffa (Fast Folding Algorithm)"),
-                       (args.deorbit_par is not None, "--deorbit-par (PINT)")]:
+    for flag, name in [(args.deorbit_par is not None, "--deorbit-par (PINT)")]:
         if flag:
             raise NotImplementedError(f"{name} is outside the B200 search hot path (SURVEY.md section 8f)")
 
@@ -788,6 +816,8 @@ def _common_main(args, func):
             out_fname += f"_{fmin:g}-{fmax:g}Hz"
         if args.fast:
             out_fname += "_fast"
+        elif args.ffa:
+            out_fname += "_ffa"
         if args.mean_fdot is not None and not np.isclose(args.mean_fdot * 1e10, 0):
             out_fname += f"_fd{args.mean_fdot * 1e10:g}e-10s-2"
 
@@ -818,10 +848,10 @@ def _common_main(args, func):
             if _dist.rank() == 0:
                 np.savez(out_fname + "_transient.npz", nave=tr.nave, freqs=tr.freqs, times=tr.times,
                          stats=np.asarray(tr.stats), f0=tr.f0, f1=tr.f1, fdot=tr.fdot, oversample=tr.oversample)
-            if not args.fast:
+            if not args.fast and not args.ffa:
                 continue
 
-        if not args.fast:
+        if not args.fast and not args.ffa:
             fdotmin = args.fdotmin if args.fdotmin is not None else 0
             fdotmax = args.fdotmax if args.fdotmax is not None else 0
             results = folding_search(
@@ -829,7 +859,7 @@ def _common_main(args, func):
                 expocorr=args.expocorr, fdotmin=fdotmin, fdotmax=fdotmax, segment_size=args.segment_size, **kwargs,
             )
             ref_time = events.gti[0, 0]
-        else:
+        elif args.fast:
             fdotmin = args.fdotmin if args.fdotmin is not None else 0
             fdotmax = args.fdotmax if args.fdotmax is not None else 0
             search_fdot = True
@@ -845,6 +875,13 @@ def _common_main(args, func):
                 force_memmap=args.force_memmap,
             )
             ref_time = (events.time[-1] + events.time[0]) / 2
+        elif args.ffa:
+            warnings.warn(
+                "The Fast Folding Algorithm functionality is experimental. Use"
+                " with care, and feel free to report any issues."
+            )
+            results = search_with_ffa(events.time, args.fmin, args.fmax, nbin=args.nbin, n=n)
+            ref_time = events.time[0]
 
         length = events.time.max() - events.time.min()
         segment_size = np.min([length, args.segment_size])
@@ -856,7 +893,7 @@ def _common_main(args, func):
         elif len(results) == 6:
             frequencies, fdots, stats, step, fdotsteps, length = results
 
-        if length > args.dynstep and not args.fast:
+        if length > args.dynstep and not (args.fast or args.ffa):
             # efsearch.py:1912-1922: the reference runs the dynamical search here, draws "Dyn.png" with matplotlib
             # and discards the arrays.  Without matplotlib the arrays the figure is drawn from are saved instead.
             from . import dist as _dist
@@ -889,7 +926,7 @@ def _common_main(args, func):
             warnings.warn("No peaks detected")
         elif args.fit_candidates and np.ndim(frequencies) > 1:
             warnings.warn("Candidate fitting is only available for 1-d (frequency-only) searches")
-        elif args.fit_candidates and not args.fast:
+        elif args.fit_candidates and not (args.fast or args.ffa):
             search_width = 5 * oversample * step
             for f in best_peaks:
                 good = np.abs(frequencies - f) < search_width

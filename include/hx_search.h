@@ -172,6 +172,29 @@ int hx_topk(const double *stats, int64_t n, int k, int64_t *idx, double *val, in
 int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double *h_val, int64_t *n_out,
                 void *stream); /* synchronizes `stream`; idx/val are HOST buffers */
 
+/* ---- fast folding algorithm (--ffa) ---------------------------------------------------------
+ * hx_hist1d_dev replaces hendrics/base.py:621-660 (`histogram` / `hist1d_numba_seq`, unweighted) as called by
+ * `search_with_ffa` (hendrics/efsearch.py:1131-1136): counts[int((x - lo) * delta)] += 1 for 0 <= (x - lo) * delta <
+ * bins, delta = 1 / ((hi - lo) / bins) -- right edge excluded.  d_counts[bins] is overwritten.
+ * hx_rebin_u32_dev replaces `_quick_rebin` (hendrics/ffa.py:352-363): d_out[i] = sum(d_in[i*rebin .. i*rebin+rebin-1]),
+ * i < n_in / rebin.
+ * hx_ffa[_dev] replaces `ffa` / `_ffa` / `ffa_step` (hendrics/ffa.py:291-349): the light curve counts[n_raw] is
+ * zero-padded to ntables x bin_period (ntables = 2^ceil(log2(n_raw / bin_period + 1)), computed by the caller like
+ * ffa.py:340), folded in log2(ntables) steps and stats[i] = Z^2_nharm of table i (trial period bin_period +
+ * i / (ntables - 1) bins); all-zero tables give NaN like the reference.  tab is a HOST array [2][nharm][bin_period]:
+ * the cos (tab[0]) and sin (tab[1]) value harmonic h+1 multiplies bin j with, i.e. the stride-(h+1) slices of the
+ * reference's tiled tables (ffa.py:98-102, 320-328; the caller builds them with numpy exactly as the reference does,
+ * including the off-by-one length of np.arange(0, 1, 1/bin_period) for some periods).  Counts are uint32 (the
+ * reference adds integer-valued doubles: same numbers).  The _dev variants take device pointers and a CUDA stream;
+ * hx_ffa_dev synchronizes the stream.
+ */
+int hx_hist1d_dev(const double *d_x, int64_t n, double lo, double hi, int64_t bins, uint32_t *d_counts, void *stream);
+int hx_rebin_u32_dev(const uint32_t *d_in, int64_t n_in, int64_t rebin, uint32_t *d_out, void *stream);
+int hx_ffa(const uint32_t *counts, int64_t n_raw, int64_t bin_period, int nharm, const double *tab, double *stats,
+           int64_t ntables, int device);
+int hx_ffa_dev(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, int nharm, const double *tab,
+               double *d_stats, int64_t ntables, void *stream);
+
 /* ---- measurement helpers --------------------------------------------------------------------
  * FP64 pipe issue-rate microbenchmarks used as the roofline denominator:
  *   kind 0: dependent-free DFMA chain      -> *ops_per_s = FP64 instructions/s (1 per DFMA)
@@ -207,7 +230,12 @@ int hx_fold_last_kernel_shape(int *R, int *mode, int *rowfd, int *m2t, double *f
  * and their number. */
 int hx_qffa_last_kernel_ms(double *ms, int64_t *launches);
 
+/* Device time of the most recent hx_ffa* call (all passes + statistics), the number of passes over HBM, of folding
+ * steps, and the steps fused per pass (0: per-step fallback). */
+int hx_ffa_last_kernel_ms(double *ms, int64_t *passes, int64_t *steps, int64_t *steps_per_pass);
+
 /* ---- tuning hooks (tests / benchmarks only; 0 restores the built-in heuristics) ------------- */
+int hx_ffa_set_tuning(int steps_per_pass); /* > 0: steps fused per pass; -1: one step per launch through HBM */
 int hx_fold_set_tuning(int trials_per_thread, int warps_per_cta);
 int hx_qffa_set_tuning(int centres_per_pass);
 /* force_generic bit 0: never use the pre-scaled fast bin path; bit 1: fp64 cells even for integer weights;

@@ -18,6 +18,8 @@ What it restates (file:line are relative to the reference tree, ``/root/referenc
     hendrics/efsearch.py:407-650   ``_average_and_z_sub_search`` / ``_transient_search_step`` / ``transient_search``
     hendrics/efsearch.py:199-205   ``check_phase_error_after_casting_to_double``
     hendrics/ffa.py:38-157         cached harmonics, ``_z_n_fast_cached`` (binned Z^2_n)
+    hendrics/ffa.py:210-395        ``ffa_step`` / ``_ffa`` / ``ffa`` / ``_quick_rebin`` / ``ffa_search`` (--ffa)
+    hendrics/efsearch.py:1092-1138 ``search_with_ffa``;  hendrics/base.py:621-660 ``hist1d_numba_seq``
     hendrics/base.py:667-693       ``_hist2d_numba_seq`` / ``hist2d_numba_seq``
     hendrics/base.py:1109-1148     ``find_peaks_in_image`` (rough / no-skimage branch)
 * out-of-tree (third-party dependency ``stingray>=2.3.2``, pyproject.toml:41, imported at
@@ -896,6 +898,164 @@ def search_best_peaks(x, stat, threshold):
         i = j
     order = np.argsort(best_stat)[::-1]
     return [best_x[o] for o in order], [best_stat[o] for o in order]
+
+
+# --------------------------------------------------------------------------------------
+# Fast folding algorithm (HENzsearch/HENefsearch --ffa): hendrics/ffa.py:210-395,
+# hendrics/efsearch.py:1092-1138, hendrics/base.py:621-630 (1-D histogram).  In-tree code, so this
+# section is PINNED: tests/golden/ffa_*.npz come from the reference's own functions.
+# --------------------------------------------------------------------------------------
+@njit()
+def _hist1d_seq(H, tracks, bins, lo, hi):
+    """hendrics/base.py:621-630 (right edge excluded, truncating index)."""
+    delta = 1 / ((hi - lo) / bins)
+    for t in range(tracks.size):
+        i = (tracks[t] - lo) * delta
+        if 0 <= i < bins:
+            H[int(i)] += 1
+    return H
+
+
+def histogram(a, bins, range):
+    """hendrics/base.py:633-660, 947-972 (unweighted numba variant; counts come back in a.dtype)."""
+    a = np.asarray(a, dtype=np.float64)
+    return _hist1d_seq(np.zeros(int(bins), dtype=np.float64), a, int(bins), float(range[0]), float(range[1]))
+
+
+@njit()
+def ffa_step_pow(step):
+    """hendrics/ffa.py:234-236."""
+    return 2 ** (step + 1)
+
+
+@njit()
+def ffa_shift(prof_n, step):
+    """hendrics/ffa.py:239-241."""
+    return (prof_n % ffa_step_pow(step) + 1) // 2
+
+
+@njit()
+def ffa_start_value(prof_n, step):
+    """hendrics/ffa.py:244-267."""
+    val = 0
+    sp = ffa_step_pow(step)
+    val += prof_n // sp * sp
+    if step >= 1:
+        val += (prof_n - val) // 2
+    return val
+
+
+@njit()
+def ffa_step(array, step, ntables):
+    """hendrics/ffa.py:291-308: table prof_n of the next level = table `start` + table `start + 2**step` rolled by
+    -shift (roll(a, -s)[j] == a[(j + s) % n], ffa.py:215-231)."""
+    out = np.copy(array)
+    jump = 2**step
+    nb = array.shape[1]
+    for prof_n in range(ntables):
+        start = ffa_start_value(prof_n, step)
+        sh = ffa_shift(prof_n, step) % nb
+        for j in range(nb):
+            jj = j + sh
+            if jj >= nb:
+                jj -= nb
+            out[prof_n, j] = array[start, j] + array[start + jump, jj]
+    return out
+
+
+def _ffa(array_reshaped, bin_period, ntables, z_n_n=2):
+    """hendrics/ffa.py:311-334."""
+    periods = np.array([bin_period + n / (ntables - 1) for n in range(ntables)])
+    for step in range(int(np.log2(ntables))):
+        array_reshaped = ffa_step(array_reshaped, step, ntables)
+    # the reference builds its tables with np.arange(0, 1, 1 / nbin), whose length is nbin or nbin + 1 depending on
+    # the rounding of 1 / nbin; the tiling below (and hence harmonic k >= 2) inherits that -- kept as is.
+    twopiphases = np.pi * 2 * np.arange(0, 1, 1 / array_reshaped.shape[1])
+    cached_cos = np.tile(np.cos(twopiphases), z_n_n)
+    cached_sin = np.tile(np.sin(twopiphases), z_n_n)
+    stats = np.zeros(ntables)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(array_reshaped.shape[0]):
+            # argument order as at ffa.py:332 (cos and sin swapped w.r.t. the signature; symmetric)
+            stats[i] = _z_n_fast_cached(array_reshaped[i, :], cached_cos, cached_sin, z_n_n)
+    return periods, stats
+
+
+def ffa_tables(bin_period, z_n_n=2):
+    """The (cos, sin) values harmonic k = 1..z_n_n of `_ffa` multiplies bin j with: tab[0, k-1, j], tab[1, k-1, j]
+    (stride-k slices of the tiled tables, ffa.py:98-102, 320-328)."""
+    twopiphases = np.pi * 2 * np.arange(0, 1, 1 / bin_period)
+    cc = np.tile(np.cos(twopiphases), z_n_n)
+    ss = np.tile(np.sin(twopiphases), z_n_n)
+    N = bin_period
+    tab = np.zeros((2, z_n_n, N))
+    for k in range(1, z_n_n + 1):
+        tab[0, k - 1] = cc[: N * k : k]
+        tab[1, k - 1] = ss[: N * k : k]
+    return tab
+
+
+def ffa(array, bin_period, z_n_n=2):
+    """hendrics/ffa.py:337-349."""
+    N_raw = len(array)
+    ntables = int(2 ** np.ceil(np.log2(N_raw // bin_period + 1)))
+    if ntables <= 1:
+        return np.zeros(1), np.zeros(1)
+    N = ntables * bin_period
+    new_arr = np.zeros(N)
+    new_arr[:N_raw] = array
+    return _ffa(new_arr.reshape([ntables, bin_period]), bin_period, ntables, z_n_n=z_n_n)
+
+
+def _quick_rebin(counts, current_rebin):
+    """hendrics/ffa.py:352-363."""
+    n = int(counts.size // current_rebin)
+    return np.sum(counts[: n * current_rebin].reshape(n, current_rebin), axis=1)
+
+
+def ffa_search(counts, dt, period_min, period_max):
+    """hendrics/ffa.py:366-395 (always Z^2_2: `ffa` is called without z_n_n)."""
+    counts = np.array(counts)
+    pmin = np.floor(period_min / dt)
+    pmax = np.ceil(period_max / dt)
+    bin_periods = None
+    stats = None
+    current_rebin = 1
+    rebinned_counts = counts
+    for bin_period in np.arange(pmin, pmax + 1, dtype=int):
+        rebin = int(2 ** np.floor(np.log2(bin_period / pmin)))
+        if rebin > current_rebin:
+            current_rebin = rebin
+            rebinned_counts = _quick_rebin(counts, current_rebin)
+        if bin_period % current_rebin != 0:
+            continue
+        per, st = ffa(rebinned_counts, bin_period // current_rebin)
+        per *= current_rebin
+        if per[0] == 0:
+            continue
+        elif bin_periods is None:
+            bin_periods = per[:-1] * dt
+            stats = st[:-1]
+        else:
+            bin_periods = np.concatenate((bin_periods, per[:-1] * dt))
+            stats = np.concatenate((stats, st[:-1]))
+    return bin_periods, stats
+
+
+def search_with_ffa(times, f0, f1, nbin=16, n=1, t0=None, t1=None):
+    """hendrics/efsearch.py:1092-1138 (`n` is accepted and ignored, as in the reference)."""
+    times = np.asarray(times)
+    if t0 is None:
+        t0 = times[0]
+    if t1 is None:
+        t1 = times[-1]
+    length = (t1 - t0).astype(np.double)
+    p0 = 1 / f1
+    p1 = 1 / f0
+    dt = p0 / nbin
+    counts = histogram((times - t0).astype(np.double), range=[0, length], bins=int(np.rint(length / dt)))
+    bin_periods, stats = ffa_search(counts, dt, p0, p1)
+    return 1 / bin_periods, stats, None, length
 
 
 # --------------------------------------------------------------------------------------

@@ -12,7 +12,8 @@ IN-TREE reference code (numpy/numba only) and runs unmodified:
                        search_with_qffa_step, search_with_qffa, z_n_fast, folding_search,
                        _average_and_z_sub_search, transient_search,
                        check_phase_error_after_casting_to_double
-    hendrics.ffa:      _z_n_fast_cached, z_n_fast_cached, z_n_fast_cached_all, h_test
+    hendrics.ffa:      _z_n_fast_cached, z_n_fast_cached, z_n_fast_cached_all, h_test, ffa, ffa_search
+    hendrics.efsearch: search_with_ffa (-> hendrics.base.histogram / hist1d_numba_seq)
     hendrics.base:     hist2d_numba_seq / histogram2d, find_peaks_in_image(rough=True)
 
 The stingray functions (z_n_search, epoch_folding_search) are NOT available: that boundary stays
@@ -172,8 +173,29 @@ def main():
     out["transient_np96"] = dict(times=ts, nave=np.asarray(tr.nave), freqs=np.asarray(tr.freqs), tgrid=np.asarray(tr.times),
                                  stats=np.asarray(tr.stats))
 
+    # ---- 8. fast folding algorithm, --ffa (in-tree: ffa.py:210-395, efsearch.py:1092-1138) -------
+    hffa.show_progress = lambda x: x
+    rng = np.random.default_rng(8)
+    counts = rng.poisson(2.0, 6000).astype(np.float64)
+    counts[1000:1300] = 0  # a data gap
+    # 49: np.arange(0, 1, 1/49) has 50 elements, so the reference's tiled harmonic tables are skewed for k = 2
+    for bp in (16, 37, 49, 128):
+        per, st = hffa.ffa(counts, bp)
+        out[f"ffa_single_{bp}"] = dict(counts=counts, bin_period=np.array([bp]), periods=per, stats=st)
+    per, st = hffa.ffa_search(counts, 0.01, 0.33, 0.7)  # period range > 2x: the rebinning branch runs
+    out["ffa_search"] = dict(counts=counts, params=np.array([0.01, 0.33, 0.7]), periods=per, stats=st)
+    ts = simulate_events(20000, 200.0, seed=21) + 8e7
+    res = hef.search_with_ffa(ts, 9.85, 9.95, nbin=16, n=2)
+    out["ffa_events"] = dict(times=ts, params=np.array([9.85, 9.95, 16, 2]), freqs=np.asarray(res[0]), stats=np.asarray(res[1]),
+                             length=np.array([res[3]]))
+    res = hef.search_with_ffa(ts[:6000], 3.1, 3.4, nbin=24, n=1)
+    out["ffa_events_nbin24"] = dict(times=ts[:6000], params=np.array([3.1, 3.4, 24, 1]), freqs=np.asarray(res[0]),
+                                    stats=np.asarray(res[1]), length=np.array([res[3]]))
+
+    only = sys.argv[1] if len(sys.argv) > 1 else ""  # `make_golden.py ffa`: (re)write only the fixtures with that prefix
     for name, d in out.items():
-        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **d)
+        if name.startswith(only):
+            np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **d)
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"wrote {len(out)} fixtures, {total / 1e6:.2f} MB")
 

@@ -76,7 +76,7 @@ def test_cli_errors(evfile):
     with pytest.warns(UserWarning, match="The number of bins is too small"):
         main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "-n", "2", "-N", "2", "--fast"])
     with pytest.raises(NotImplementedError):
-        main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "--ffa"])
+        main_zsearch([evfile, "-f", "9.85", "-F", "9.95", "--deorbit-par", "nonexistent.par"])
 
 
 def test_transient_cli(evfile):
@@ -133,3 +133,24 @@ def test_cli_runs_the_dynamical_search(evfile, tmp_path, monkeypatch):
     # every window is the direct search of its events, from the oracle
     sel = ev.time[(ev.time >= 8e7 + 5.0) & (ev.time < 8e7 + 10.0)]
     np.testing.assert_allclose(d["stats"][1], O.z_n_search(sel, f, nharm=2, nbin=128)[1], rtol=1e-9)
+
+
+def test_zsearch_ffa_cli(evfile):
+    """hendrics/tests/test_efsearch.py:557-581 (`--ffa`): output name, experimental warning, pulse recovered"""
+    from hendrics_b200.efsearch import main_zsearch
+    from hendrics_b200.io import load_folding
+
+    with pytest.warns(UserWarning, match="Fast Folding Algorithm functionality is experimental"):
+        out = main_zsearch([evfile, "-f", "9.89", "-F", "9.92", "-n", "64", "--ffa", "--find-candidates"])
+    assert len(out) == 1 and out[0].endswith("events_Z22_9.89-9.92Hz_ffa.p") and os.path.exists(out[0])
+    ef = load_folding(out[0])
+    assert ef.kind == "Z2n" and ef.nbin == 64
+    best = ef.freq[np.nanargmax(ef.stat)]
+    assert np.isclose(best, PULSE_F, atol=1 / 25.25)
+    # same numbers as the oracle's restatement of search_with_ffa on the same events
+    ts = O.simulate_events(10000, 25.25, seed=42) + 8e7
+    fr, st, _, _ = O.search_with_ffa(ts, 9.89, 9.92, nbin=64, n=2)
+    assert np.array_equal(ef.freq, fr)
+    ok = ~np.isnan(st)
+    assert np.array_equal(np.isnan(ef.stat), ~ok)
+    np.testing.assert_allclose(ef.stat[ok], st[ok], rtol=1e-9)

@@ -1,0 +1,78 @@
+"""CPU: the FFA oracle (oracle/hx_oracle.py) against golden vectors produced by the REAL reference code
+(hendrics/ffa.py, hendrics/efsearch.py:search_with_ffa; tests/golden/make_golden.py section 8)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hx_oracle as ho
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SINGLE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "ffa_single_*.npz")))
+
+
+def load(name):
+    with np.load(os.path.join(GOLD, name + ".npz")) as d:
+        return {k: d[k] for k in d.files}
+
+
+def same(a, b, rtol):
+    """equal NaN pattern (all-zero tables) and values within rtol"""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    np.testing.assert_allclose(a[ok], b[ok], rtol=rtol, atol=0)
+
+
+def test_ffa_index_helpers_known_answers():
+    # doctests of hendrics/ffa.py:244-256
+    assert ho.ffa_start_value(0, 0) == 0 and ho.ffa_start_value(4, 0) == 4 and ho.ffa_start_value(5, 2) == 2
+    assert ho.ffa_start_value(8, 1) == 8 and ho.ffa_start_value(7, 1) == 5 and ho.ffa_start_value(10, 2) == 9
+    # the table in the module docstring of hendrics/ffa.py:9-25: step 1, prof 3 = 1 + 3'' ; step 2, prof 7 = 3 + 7''''
+    assert (ho.ffa_start_value(3, 1), ho.ffa_shift(3, 1)) == (1, 2)
+    assert (ho.ffa_start_value(7, 2), ho.ffa_shift(7, 2)) == (3, 4)
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_ffa_single_oracle_vs_reference(name):
+    g = load(name)
+    per, st = ho.ffa(g["counts"], int(g["bin_period"][0]))
+    assert np.array_equal(per, g["periods"])
+    same(st, g["stats"], 1e-12)
+
+
+def test_ffa_search_oracle_vs_reference():
+    g = load("ffa_search")
+    dt, p0, p1 = g["params"]
+    per, st = ho.ffa_search(g["counts"], dt, p0, p1)
+    assert np.array_equal(per, g["periods"])
+    same(st, g["stats"], 1e-12)
+
+
+@pytest.mark.parametrize("name", ["ffa_events", "ffa_events_nbin24"])
+def test_search_with_ffa_oracle_vs_reference(name):
+    g = load(name)
+    f0, f1, nbin, n = g["params"]
+    fr, st, _, length = ho.search_with_ffa(g["times"], f0, f1, nbin=int(nbin), n=int(n))
+    assert np.array_equal(fr, g["freqs"]) and length == g["length"][0]
+    same(st, g["stats"], 1e-12)
+
+
+def test_ffa_recovers_the_pulse():
+    # behaviour the reference tests for (hendrics/tests/test_ffa.py:10-31): the best period is the injected one
+    g = load("ffa_events")
+    best = g["freqs"][np.nanargmax(g["stats"])]
+    assert abs(best - 1 / 0.101) < 5e-3
+
+
+def test_ffa_tables_reproduce_the_arange_quirk():
+    # np.arange(0, 1, 1/49) has 50 elements: harmonic 2 of the reference reads a skewed table for such periods
+    assert len(np.arange(0, 1, 1 / 49)) == 50
+    tab = ho.ffa_tables(49, 2)
+    j = np.arange(49)
+    np.testing.assert_allclose(tab[0, 0], np.cos(2 * np.pi * j / 49), atol=1e-15)
+    assert not np.allclose(tab[0, 1], np.cos(4 * np.pi * j / 49))  # the quirk
+    tab = ho.ffa_tables(37, 2)
+    np.testing.assert_allclose(tab[0, 1], np.cos(4 * np.pi * np.arange(37) / 37), atol=1e-14)
