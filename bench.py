@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the HENDRICS periodicity-search hot path on B200 ("Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c5|w1|w2] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c5|w1|w2|ffa] [--impl reference]
 
 One "step" = one pass of the search over this rank's slice of the trial grid on a synthetic
 HENfake-style event list.  Default workload = BASELINE.json configs[1] (C2: HENefsearch, epoch
@@ -356,6 +356,168 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+# --ffa (widening row: hendrics/ffa.py, efsearch.py:1092-1138): the whole `search_with_ffa` of a C4-like event list.
+# (description, n_events, T, f0, f1, nbin)
+FFA = ("FFA: HENzsearch --ffa -f 9.89 -F 9.95 -n 128 on 1e8 events over 1e5 s: 1.27e8-bin light curve, 2^20 tables x "
+       "128..129 bins, 20 folding steps per trial bin period", 100_000_000, 1e5, 9.89, 9.95, 128)
+FFA_UNIT = "bin*steps/s"
+FFA_METRIC = "fast-folding search throughput (light-curve bins x folding steps per second)"
+
+
+def ffa_inputs():
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, f0, f1, nbin = FFA
+    ts = simulate_events(n_ev, T, seed=6)
+    return desc, ts, f0, f1, nbin
+
+
+def ffa_units(n_bins, nbin, f0, f1):
+    """table elements x folding steps summed over the integer bin periods of the search (ffa.py:366-395, no rebinning
+    for f1/f0 < 2)"""
+    p0, p1 = 1 / f1, 1 / f0
+    dt = p0 / nbin
+    tot = 0.0
+    for bp in range(int(np.floor(p0 / dt)), int(np.ceil(p1 / dt)) + 1):
+        ntab = int(2 ** np.ceil(np.log2(n_bins // bp + 1)))
+        tot += float(ntab) * bp * np.log2(ntab)
+    return tot
+
+
+def run_ffa_reference(args):
+    """CPU arm: the oracle's restatement of search_with_ffa (numba, as the reference) on a bounded sample."""
+    from oracle import hx_oracle as O
+
+    desc, n_ev, T, f0, f1, nbin = FFA
+    n_s, T_s = 1_000_000, 1e3  # same rate, 1 % of the exposure: 2^13 tables, 13 steps
+    from hendrics_b200.fake import simulate_events
+    ts = simulate_events(n_s, T_s, seed=6)
+    O.search_with_ffa(ts[:20000], f0, f1, nbin=nbin)  # numba compilation
+    times = []
+    for _ in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.search_with_ffa(ts, f0, f1, nbin=nbin)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times[args.warmup:]))
+    n_bins = int(np.rint((ts[-1] - ts[0]) / (1 / f1 / nbin)))
+    v = ffa_units(n_bins, nbin, f0, f1) / dt
+    line = {"impl": "reference", "metric": FFA_METRIC, "value": v, "unit": FFA_UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": {"workload": desc, "nbin": nbin},
+            "cpu_baseline": {"value": v, "unit": FFA_UNIT, "cores": 1, "kind": "port",
+                             "sample": f"search_with_ffa on {n_s} events over {T_s:g} s (serial numba loops, like the reference)"},
+            "e2e": {"value": v, "unit": FFA_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ffa(args):
+    """--ffa: value = the FFAs of the search on a device-resident light curve; e2e = search_with_ffa from host events."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    from hendrics_b200 import _cabi
+    from hendrics_b200.efsearch import search_with_ffa
+    from hendrics_b200.ffa import ffa_search
+
+    desc, ts, f0, f1, nbin = ffa_inputs()
+    dev = torch.device("cuda", local_rank)
+    p0, p1 = 1 / f1, 1 / f0
+    dt = p0 / nbin
+    length = float(ts[-1] - ts[0])
+    bins = int(np.rint(length / dt))
+    x = torch.from_numpy(ts - ts[0]).to(dev)
+    counts = torch.empty(bins, dtype=torch.int32, device=dev)
+    _cabi.check(_cabi.lib().hx_hist1d_dev(x.data_ptr(), x.numel(), 0.0, 0.0, length, bins, counts.data_ptr(), 0))
+    torch.cuda.synchronize()
+    units = ffa_units(bins, nbin, f0, f1)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    kern = []
+    def step_resident():
+        # the loop of ffa_search, keeping the device time of every hx_ffa_dev call
+        ms = 0.0
+        from hendrics_b200.ffa import _ffa_device
+        for bp in range(int(np.floor(p0 / dt)), int(np.ceil(p1 / dt)) + 1):
+            _ffa_device(counts, bp)
+            k = _cabi.ffa_last_kernel()
+            ms += k[0]
+        kern.append((ms, k[1], k[2], k[3]))
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    kern.clear()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_s = sum(step_ms) * 1e-3
+    value = units * world * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    pin = torch.from_numpy(ts).pin_memory().numpy()
+    search_with_ffa(pin, f0, f1, nbin=nbin)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fr, st, _, _ = search_with_ffa(pin, f0, f1, nbin=nbin)
+    torch.cuda.synchronize()
+    e2e_value = units * world * args.steps / (time.perf_counter() - t0)
+
+    if rank == 0:
+        k_ms = float(np.mean([m for m, *_ in kern]))
+        passes, steps, kk = kern[-1][1:]
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_gbs = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        achieved = 8.0 * units / (k_ms * 1e-3) / 1e9  # one read + one write of every table element per step
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+            "kernel": "hx::ffa_pass_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
+            "algorithmic_bytes_per_bin_step": 8, "passes_over_hbm_per_ffa": int(passes), "steps_per_ffa": int(steps),
+            "steps_fused_per_pass": int(kk), "streamed_gbs": achieved * passes / steps,
+            "note": "k folding steps are fused per pass in shared memory, so HBM sees 8 B per bin and PASS, not per step: frac "
+                    "counts the step-by-step algorithm's bytes and exceeds the traffic actually drawn (streamed_gbs); the "
+                    "fused kernel is bound by the shared-memory pipe / instruction issue of the in-SM fold (DESIGN.md K5)",
+            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if os.path.exists(peaks_file) else "fallback",
+        }
+        line = {
+            "metric": FFA_METRIC, "value": value, "unit": FFA_UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": desc, "nbin": nbin, "n_events": int(ts.size), "light_curve_bins": bins,
+                       "parallelism": "replicas only (a search has 2-3 bin periods; nothing to shard)",
+                       "l2": "light curve (0.5 GB) exceeds L2; L2 also flushed between timed iterations"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": FFA_UNIT, "h2d_bytes_per_step": int(ts.nbytes), "d2h_bytes_per_step": int(st.nbytes)},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import hx_oracle as O
+            from hendrics_b200.fake import simulate_events
+            tsamp = simulate_events(1_000_000, 1e3, seed=6)
+            O.search_with_ffa(tsamp[:20000], f0, f1, nbin=nbin)
+            t0 = time.perf_counter()
+            O.search_with_ffa(tsamp, f0, f1, nbin=nbin)
+            dtc = time.perf_counter() - t0
+            nb = int(np.rint((tsamp[-1] - tsamp[0]) / dt))
+            line["cpu_baseline"] = {"value": ffa_units(nb, nbin, f0, f1) / dtc, "unit": FFA_UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"search_with_ffa on 1e6 events over 1e3 s (same rate, 1 % of the exposure), {dtc:.1f} s; "
+                                              "serial numba loops like the reference"}
+        print(json.dumps(line), flush=True)
+
+
 # Weighted / exposure-corrected fold (K1w; SURVEY 8f rank 3): light-curve input (weights = counts per bin) and `--expocorr`.
 # name -> (description, n_bins_or_events, T, n_freq per GPU, f_start, f_step, nbin, nharm, weights, n_gti, seed)
 WEIGHTED = {
@@ -568,11 +730,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"] + sorted(WEIGHTED))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = args.workload
+    if wl == "ffa":
+        return run_ffa_reference(args) if args.impl == "reference" else run_ffa(args)
     if wl in WEIGHTED:
         return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
     if args.impl == "reference":

@@ -49,7 +49,7 @@ SIGNATURES = {
     "hx_zn_unbinned_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
-    "hx_hist1d_dev": (_int, [_vp, _i64, _dbl, _dbl, _i64, _vp, _vp]),
+    "hx_hist1d_dev": (_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp]),
     "hx_rebin_u32_dev": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "hx_ffa": (_int, [_c_u32p, _i64, _i64, _int, _c_dp, _c_dp, _i64, _int]),
     "hx_ffa_dev": (_int, [_vp, _i64, _i64, _int, _c_dp, _vp, _i64, _vp]),

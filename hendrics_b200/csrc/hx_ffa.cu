@@ -72,36 +72,40 @@ __device__ __forceinline__ double ffa_row_stat(const uint32_t *row, int P, int n
 }
 
 // Persistent CTAs: tile t+1 (the 2^k tables of the next working set) is prefetched with asynchronous copies (LDGSTS)
-// into the second load buffer while tile t is folded, so every resident CTA always has a tile of HBM reads in flight
-// (the first, load -> fold -> store version left HBM idle two thirds of the time: 1.4 TB/s).
-// Shared memory: two load buffers + one work buffer of 2^k x P counts (+ the harmonic tables on the last pass).
+// into the second load buffer while tile t is folded.
+// Shared memory: two load buffers + one work buffer of 2^k tables at a row stride of Ps = ceil4(P) counts (16-byte aligned
+// rows whatever P), + the harmonic tables on the last pass.
+// Fold step: 4 bins per lane and trip, all loads of a trip in flight before the first add, 32-bit shared-window
+// addresses.  (The first version -- one bin per lane and trip, generic pointers, a 64-bit modulo per table -- was bound by
+// instruction issue at 1 warp-instruction per bin and step; ncu history in DESIGN.md.)
 __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int P = a.P, k = a.k, s0 = a.s0;
+    const int Ps = (P + 3) & ~3, nvec = Ps >> 2;
     const int nrow = 1 << k;
-    const size_t tile_el = (size_t)nrow * P;
-    uint32_t *ld0 = reinterpret_cast<uint32_t *>(smem_raw);  // load buffers: ld0, ld0 + tile_el
-    uint32_t *work = ld0 + 2 * tile_el;
-    double *stab = reinterpret_cast<double *>(work + tile_el);  // last pass only (8-byte aligned: 3*nrow*P*4)
+    const uint32_t tile_bytes = (uint32_t)nrow * (uint32_t)Ps * 4u;
+    const uint32_t s_ld0 = smem_u32(smem_raw);  // load buffers: s_ld0, s_ld0 + tile_bytes; work buffer behind them
+    const uint32_t s_work = s_ld0 + 2u * tile_bytes;
+    double *stab = reinterpret_cast<double *>(smem_raw + 3 * (size_t)tile_bytes + 512);  // last pass only
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool last = a.dst == nullptr;
     const long long ntiles = a.ntables >> k;
+
+    const int step32 = 32 % P;  // rotated index advance between the 4 bins of a lane (32, or 32 mod P for tiny periods)
 
     if (last)
         for (int i = threadIdx.x; i < 2 * a.nharm * P; i += blockDim.x) stab[i] = a.tab[i];
 
     // gather of tile c: local table q <- table G + q*2^s0 + h; bins beyond the raw light curve are zero-filled by the
     // copy itself (src-size 0)
-    auto issue_gather = [&](long long c, uint32_t *buf) {
+    auto issue_gather = [&](long long c, uint32_t sb) {
         const long long h = c & ((1LL << s0) - 1);
         const long long G = (c >> s0) << (s0 + k);
-        const uint32_t sb = smem_u32(buf);
-        if (a.vec4) {  // P % 4 == 0: rows are 16-byte aligned in HBM and in shared memory
-            const int P4 = P >> 2;
+        if (a.vec4) {  // P % 4 == 0: rows are 16-byte aligned in HBM too
             for (int q = warp; q < nrow; q += nwarps) {
                 const long long base = (G + ((long long)q << s0) + h) * P;
-                const uint32_t d = sb + (uint32_t)q * (uint32_t)P * 4u;
-                for (int j4 = lane; j4 < P4; j4 += 32) {
+                const uint32_t d = sb + (uint32_t)q * (uint32_t)Ps * 4u;
+                for (int j4 = lane; j4 < nvec; j4 += 32) {
                     const long long idx = base + 4LL * j4;
                     const long long left = a.n_src - idx;
                     const uint32_t nb = left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
         } else {
             for (int q = warp; q < nrow; q += nwarps) {
                 const long long base = (G + ((long long)q << s0) + h) * P;
-                const uint32_t d = sb + (uint32_t)q * (uint32_t)P * 4u;
+                const uint32_t d = sb + (uint32_t)q * (uint32_t)Ps * 4u;
                 for (int j = lane; j < P; j += 32) {
                     const long long idx = base + j;
                     const bool ok = idx < a.n_src;
@@ -123,51 +127,70 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
     };
 
     long long c = blockIdx.x;
-    if (c < ntiles) issue_gather(c, ld0);
+    if (c < ntiles) issue_gather(c, s_ld0);
     for (int it = 0; c < ntiles; it++, c += gridDim.x) {
         cp_async_wait_all();
         __syncthreads();  // tile c has landed; every thread is done with the previous tile (its buffers are free)
-        if (c + gridDim.x < ntiles) issue_gather(c + gridDim.x, ld0 + (size_t)((it + 1) & 1) * tile_el);
-        // hs = (h * 2^sg) mod P, doubled from step to step: the only 64-bit division is this one per tile (a 64-bit
-        // modulo per table and step made the first version compute-bound: 3.5 elements/clk/SM)
+        if (c + gridDim.x < ntiles) issue_gather(c + gridDim.x, s_ld0 + (uint32_t)((it + 1) & 1) * tile_bytes);
+        // hs = (h * 2^sg) mod P, doubled from step to step: the only 64-bit division is this one per tile
         uint32_t hs = (uint32_t)((c & ((1LL << s0) - 1)) % P);
 
-        uint32_t *in = ld0 + (size_t)(it & 1) * tile_el, *out = work;
+        uint32_t s_in = s_ld0 + (uint32_t)(it & 1) * tile_bytes, s_out = s_work;
         for (int sg = 0; sg < k; sg++) {
             for (int r = warp; r < nrow; r += nwarps) {
                 const int mu = r & ((2 << sg) - 1);
                 const int i1 = (r - mu) + (mu >> 1), i2 = i1 + (1 << sg);
-                const int sh = (int)((hs + (uint32_t)((mu + 1) >> 1)) % (uint32_t)P);  // < 2^24 + 2^11: 32-bit
-                const uint32_t *p1 = in + (size_t)i1 * P, *p2 = in + (size_t)i2 * P;
-                uint32_t *o = out + (size_t)r * P;
-                for (int j = lane; j < P; j += 32) {
-                    int jj = j + sh;
-                    if (jj >= P) jj -= P;
-                    o[j] = p1[j] + p2[jj];
+                uint32_t t = hs + (uint32_t)((mu + 1) >> 1);  // shift of this table, reduced mod P
+                if (t >= (uint32_t)P) {
+                    t -= (uint32_t)P;
+                    if (t >= (uint32_t)P) t %= (uint32_t)P;
+                }
+                const int sh = (int)t;
+                const uint32_t a1 = s_in + (uint32_t)i1 * (uint32_t)Ps * 4u, a2 = s_in + (uint32_t)i2 * (uint32_t)Ps * 4u;
+                const uint32_t ao = s_out + (uint32_t)r * (uint32_t)Ps * 4u;
+                // 4 bins per lane and trip at a lane stride of one word (bins j0, j0+32, j0+64, j0+96): every LDS / STS of
+                // the warp touches 32 consecutive words -- conflict-free.  (128-bit accesses for the unrotated table with
+                // four 16-byte-strided LDS.32 for the rotated one cost twice the wavefronts: 4-way bank conflicts, ncu.)
+                for (int j0 = lane; j0 < P; j0 += 128) {
+                    int e = j0 + sh;
+                    if (e >= P) e -= P;
+                    uint32_t x[4], y[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        x[u] = lds_u32(a1 + (uint32_t)((j0 + 32 * u) << 2));  // may read up to 96 words past a short row: in-bounds
+                        y[u] = lds_u32(a2 + (uint32_t)(e << 2));
+                        e += step32;
+                        if (e >= P) e -= P;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j0 + 32 * u < P) sts_u32(ao + (uint32_t)((j0 + 32 * u) << 2), x[u] + y[u]);
                 }
             }
             __syncthreads();
-            uint32_t *t = in;
-            in = out, out = t;
+            const uint32_t tmp = s_in;
+            s_in = s_out, s_out = tmp;
             hs <<= 1;
             if (hs >= (uint32_t)P) hs -= (uint32_t)P;
         }
 
-        // `in` now holds tables c*2^k .. c*2^k + 2^k - 1 of the next level
+        // s_in now holds tables c*2^k .. c*2^k + 2^k - 1 of the next level
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(smem_raw + (s_in - s_ld0));
         if (last) {
             for (int r = warp; r < nrow; r += nwarps) {
-                const double z = ffa_row_stat(in + (size_t)r * P, P, a.nharm, stab, lane);
+                const double z = ffa_row_stat(in + (size_t)r * Ps, P, a.nharm, stab, lane);
                 if (lane == 0) a.stats[c * nrow + r] = z;
             }
         } else {
-            uint32_t *d = a.dst + (size_t)c * nrow * P;  // 2^k contiguous tables
-            const int n = nrow * P;
+            uint32_t *d = a.dst + (size_t)c * nrow * P;  // 2^k contiguous tables (row stride P in HBM)
             if (a.vec4) {
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(in);
                 uint4 *d4 = reinterpret_cast<uint4 *>(d);
-                for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) d4[i] = s4[i];
+                const int n4 = nrow * nvec;
+                for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
             } else {
-                for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = in[i];
+                for (int q = warp; q < nrow; q += nwarps)
+                    for (int j = lane; j < P; j += 32) d[(size_t)q * P + j] = in[(size_t)q * Ps + j];
             }
         }
     }
@@ -208,11 +231,12 @@ __global__ void __launch_bounds__(256) ffa_stat_global_kernel(const uint32_t *__
 
 // ---- 1-D histogram and rebinning ----------------------------------------------------------------------------------
 // hendrics/base.py:621-630: delta = 1/((hi-lo)/bins); i = (x-lo)*delta; counted iff 0 <= i < bins at index int(i)
-__global__ void __launch_bounds__(256) hist1d_kernel(const double *__restrict__ x, long long n, double lo, double delta,
-                                                     long long bins, uint32_t *__restrict__ H) {
+// x0: the caller's re-zeroing `(times - t0).astype(double)` (efsearch.py:1131), one more separately rounded subtraction
+__global__ void __launch_bounds__(256) hist1d_kernel(const double *__restrict__ x, long long n, double x0, double lo,
+                                                     double delta, long long bins, uint32_t *__restrict__ H) {
     const double fb = (double)bins;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const double i = __dmul_rn(__dsub_rn(x[t], lo), delta);
+        const double i = __dmul_rn(__dsub_rn(__dsub_rn(x[t], x0), lo), delta);
         if (i >= 0.0 && i < fb) atomicAdd(H + (long long)i, 1u);
     }
 }
@@ -233,7 +257,10 @@ static int g_ffa_dev = -1, g_ffa_passes = 0, g_ffa_steps = 0, g_ffa_k = 0;
 static int g_ffa_k_override = 0;  // tuning hook: steps per pass (0: heuristic; -1: force the per-step HBM fallback)
 
 static size_t pass_smem(int k, int P, int nharm, bool last) {
-    return (size_t)3 * ((size_t)1 << k) * P * 4 + (last ? (size_t)2 * nharm * P * 8 : 0);  // 2 load buffers + 1 work buffer
+    // 2 load buffers + 1 work buffer at a row stride of ceil4(P) counts, 512 bytes of slack (the 4-bins-per-lane fold reads
+    // up to 96 words past a row whose length is not a multiple of 128; those values are never stored), the harmonic
+    // tables on the last pass
+    return (size_t)3 * ((size_t)1 << k) * ((P + 3) & ~3) * 4 + 512 + (last ? (size_t)2 * nharm * P * 8 : 0);
 }
 
 int ffa_dev_impl(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, int nharm, const double *tab,
@@ -263,13 +290,14 @@ int ffa_dev_impl(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, in
     HX_CUDA_TRY(b_tab.alloc((size_t)2 * nharm * P * sizeof(double)));
     HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab, (size_t)2 * nharm * P * sizeof(double), cudaMemcpyHostToDevice, st));
 
-    // steps per pass: the largest k whose three buffers leave >= 4 CTAs per SM, else whatever fits
+    // steps per pass: the largest k whose three buffers leave >= 2 CTAs per SM (measured on B200, tools/quick_ffa.py:
+    // fewer passes beat more resident CTAs up to there), else whatever fits
     int k_fit = 0;
     for (int k = 1; k <= S && k <= 12; k++)
         if (pass_smem(k, P, nharm, true) <= (size_t)di.smem_optin) k_fit = k;
     int k_pref = 0;
     for (int k = 1; k <= k_fit; k++)
-        if (pass_smem(k, P, nharm, true) + di.reserved_smem <= (size_t)di.smem_per_sm / 4) k_pref = k;
+        if (pass_smem(k, P, nharm, true) + di.reserved_smem <= (size_t)di.smem_per_sm / 2) k_pref = k;
     if (k_pref < 3) k_pref = std::min(k_fit, 3);
     if (const char *e = getenv("HX_FFA_K")) g_ffa_k_override = atoi(e);
     int k_use = g_ffa_k_override > 0 ? std::min(g_ffa_k_override, k_fit) : k_pref;
@@ -345,7 +373,8 @@ int ffa_dev_impl(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, in
 
 extern "C" {
 
-int hx_hist1d_dev(const double *d_x, int64_t n, double lo, double hi, int64_t bins, uint32_t *d_counts, void *stream) {
+int hx_hist1d_dev(const double *d_x, int64_t n, double x0, double lo, double hi, int64_t bins, uint32_t *d_counts,
+                  void *stream) {
     std::lock_guard<std::recursive_mutex> api_lock(hx::api_mutex());
     if (!d_x || !d_counts || n < 0 || bins < 1 || !(hi > lo)) {
         hx::set_error("hx_hist1d_dev: bad arguments (n=%lld bins=%lld range=[%g, %g])", (long long)n, (long long)bins, lo, hi);
@@ -355,8 +384,8 @@ int hx_hist1d_dev(const double *d_x, int64_t n, double lo, double hi, int64_t bi
     HX_CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)bins * sizeof(uint32_t), st));
     if (n > 0) {
         const double delta = 1.0 / ((hi - lo) / (double)bins);
-        hx::hist1d_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(d_x, n, lo, delta, bins,
-                                                                                                   d_counts);
+        hx::hist1d_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(d_x, n, x0, lo, delta,
+                                                                                                   bins, d_counts);
         HX_CHECK_LAUNCH("hist1d_kernel");
     }
     return HX_OK;

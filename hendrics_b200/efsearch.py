@@ -455,11 +455,15 @@ def search_with_ffa(times, f0, f1, nbin=16, n=1, t0=None, t1=None):
     p1 = 1 / f0
     dt = p0 / nbin
     bins = int(np.rint(length / dt))
-    x = _to_device((times - t0).astype(np.double))
+    if times.dtype == np.float64:
+        # `(times - t0).astype(np.double)` is one fp64 subtraction per event: done inside the histogram kernel (x0 = t0)
+        x, x0 = _to_device(times), float(t0)
+    else:  # extended-precision times: subtract on the host in their own precision, then round, as the reference does
+        x, x0 = _to_device((times - t0).astype(np.double)), 0.0
     counts = torch.empty(bins, dtype=torch.int32, device=x.device)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     with torch.cuda.device(x.device):
-        _cabi.check(_cabi.lib().hx_hist1d_dev(x.data_ptr(), x.numel(), 0.0, float(length), bins, counts.data_ptr(), stream))
+        _cabi.check(_cabi.lib().hx_hist1d_dev(x.data_ptr(), x.numel(), x0, 0.0, float(length), bins, counts.data_ptr(), stream))
     bin_periods, stats = ffa_search(counts, dt, p0, p1)
     return 1 / bin_periods, stats, None, length
 

@@ -14,6 +14,8 @@ the sums are the same numbers.  A light curve with fractional or negative counts
 
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 from . import _cabi
@@ -111,8 +113,20 @@ def _counts_to_device(counts, device=None):
     return c
 
 
-def _ffa_device(counts_d, bin_period, z_n_n=2):
-    """``ffa`` on a device light curve: (periods, stats) as host arrays, ffa.py:337-349."""
+@functools.lru_cache(maxsize=4)
+def _period_fractions(ntables):
+    """n / (ntables - 1), n = 0 .. ntables - 1 (ffa.py:314); the same array for every bin period of a search"""
+    f = np.arange(ntables) / (ntables - 1)
+    f.setflags(write=False)
+    return f
+
+
+_PINNED = {}  # (device index, ntables) -> pinned host buffer for the statistics of one FFA
+
+
+def _ffa_device(counts_d, bin_period, z_n_n=2, reuse_host_buffer=False):
+    """``ffa`` on a device light curve: (periods, stats) as host arrays, ffa.py:337-349.  With ``reuse_host_buffer`` the
+    statistics come back as a view of a cached pinned buffer that the next call overwrites (``ffa_search`` copies them)."""
     import torch
 
     N_raw = counts_d.numel()
@@ -120,14 +134,22 @@ def _ffa_device(counts_d, bin_period, z_n_n=2):
     ntables = int(2 ** np.ceil(np.log2(N_raw // bin_period + 1)))
     if ntables <= 1:
         return np.zeros(1), np.zeros(1)
-    periods = bin_period + np.arange(ntables) / (ntables - 1)  # == [bin_period + n / (ntables - 1) ...], ffa.py:314
+    periods = bin_period + _period_fractions(ntables)  # == [bin_period + n / (ntables - 1) ...]
     tab = np.ascontiguousarray(_ffa_tables(bin_period, z_n_n))
     stats = torch.empty(ntables, dtype=torch.float64, device=counts_d.device)
     with torch.cuda.device(counts_d.device):
         stream = torch.cuda.current_stream(counts_d.device).cuda_stream
         _cabi.check(_cabi.lib().hx_ffa_dev(counts_d.data_ptr(), N_raw, bin_period, int(z_n_n), _cabi.dptr(tab),
                                            stats.data_ptr(), ntables, stream))
-    return periods, stats.cpu().numpy()
+    if not reuse_host_buffer:
+        return periods, stats.cpu().numpy()
+    key = (counts_d.device.index, ntables)
+    host = _PINNED.get(key)
+    if host is None:
+        _PINNED.clear()  # one size at a time: a search uses a single ntables (two when the light curve is rebinned)
+        host = _PINNED[key] = torch.empty(ntables, dtype=torch.float64, pin_memory=True)
+    host.copy_(stats)
+    return periods, host.numpy()
 
 
 def ffa(array, bin_period, z_n_n=2):
@@ -171,14 +193,14 @@ def ffa_search(counts, dt, period_min, period_max):
         if bin_period % current_rebin != 0:
             continue
 
-        per, st = _ffa_device(rebinned_counts, bin_period // current_rebin)
+        per, st = _ffa_device(rebinned_counts, bin_period // current_rebin, reuse_host_buffer=True)
         per = per * current_rebin
 
         if per[0] == 0:
             continue
         elif bin_periods is None:
             bin_periods = per[:-1] * dt
-            stats = st[:-1]
+            stats = st[:-1].copy()  # st is a view of a reused pinned buffer
         else:
             bin_periods = np.concatenate((bin_periods, per[:-1] * dt))
             stats = np.concatenate((stats, st[:-1]))

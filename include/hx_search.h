@@ -174,8 +174,9 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
 
 /* ---- fast folding algorithm (--ffa) ---------------------------------------------------------
  * hx_hist1d_dev replaces hendrics/base.py:621-660 (`histogram` / `hist1d_numba_seq`, unweighted) as called by
- * `search_with_ffa` (hendrics/efsearch.py:1131-1136): counts[int((x - lo) * delta)] += 1 for 0 <= (x - lo) * delta <
- * bins, delta = 1 / ((hi - lo) / bins) -- right edge excluded.  d_counts[bins] is overwritten.
+ * `search_with_ffa` (hendrics/efsearch.py:1131-1136): with v = x - x0 (the caller's re-zeroing `times - t0`, a separately
+ * rounded fp64 subtraction; pass x0 = 0 for none), counts[int((v - lo) * delta)] += 1 for 0 <= (v - lo) * delta < bins,
+ * delta = 1 / ((hi - lo) / bins) -- right edge excluded.  d_counts[bins] is overwritten.
  * hx_rebin_u32_dev replaces `_quick_rebin` (hendrics/ffa.py:352-363): d_out[i] = sum(d_in[i*rebin .. i*rebin+rebin-1]),
  * i < n_in / rebin.
  * hx_ffa[_dev] replaces `ffa` / `_ffa` / `ffa_step` (hendrics/ffa.py:291-349): the light curve counts[n_raw] is
@@ -188,7 +189,8 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  * reference adds integer-valued doubles: same numbers).  The _dev variants take device pointers and a CUDA stream;
  * hx_ffa_dev synchronizes the stream.
  */
-int hx_hist1d_dev(const double *d_x, int64_t n, double lo, double hi, int64_t bins, uint32_t *d_counts, void *stream);
+int hx_hist1d_dev(const double *d_x, int64_t n, double x0, double lo, double hi, int64_t bins, uint32_t *d_counts,
+                  void *stream);
 int hx_rebin_u32_dev(const uint32_t *d_in, int64_t n_in, int64_t rebin, uint32_t *d_out, void *stream);
 int hx_ffa(const uint32_t *counts, int64_t n_raw, int64_t bin_period, int nharm, const double *tab, double *stats,
            int64_t ntables, int device);

@@ -88,7 +88,7 @@ def test_hist1d_and_rebin_bit_exact():
     H = ho.histogram(x, bins=bins, range=[0.0, 1000.0])
     xd = torch.from_numpy(x).cuda()
     Hd = torch.empty(bins, dtype=torch.int32, device="cuda")
-    _cabi.check(_cabi.lib().hx_hist1d_dev(xd.data_ptr(), xd.numel(), 0.0, 1000.0, bins, Hd.data_ptr(), 0))
+    _cabi.check(_cabi.lib().hx_hist1d_dev(xd.data_ptr(), xd.numel(), 0.0, 0.0, 1000.0, bins, Hd.data_ptr(), 0))
     torch.cuda.synchronize()
     assert np.array_equal(Hd.cpu().numpy().astype(np.int64), H.astype(np.int64))
     for r in (2, 3, 8):
