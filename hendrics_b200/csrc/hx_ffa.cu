@@ -25,6 +25,14 @@
 
 namespace hx {
 
+// shared-memory row stride (in counts): a multiple of 4 (16-byte aligned rows whatever P) that is 4 mod 8, so that the 8
+// tables x 4 consecutive bins an FP64 MMA A-fragment reads (epilogue) fall into 32 distinct banks
+__host__ __device__ __forceinline__ int ffa_row_stride(int P) {
+    int ps = (P + 3) & ~3;
+    if ((ps & 7) != 4) ps += 4;
+    return ps;
+}
+
 struct FfaPassArgs {
     const uint32_t *src;  // first pass: the raw light curve (n_src valid bins, zero beyond); later: ntables x P tables
     long long n_src;
@@ -73,15 +81,19 @@ __device__ __forceinline__ double ffa_row_stat(const uint32_t *row, int P, int n
 
 // Persistent CTAs: tile t+1 (the 2^k tables of the next working set) is prefetched with asynchronous copies (LDGSTS)
 // into the second load buffer while tile t is folded.
-// Shared memory: two load buffers + one work buffer of 2^k tables at a row stride of Ps = ceil4(P) counts (16-byte aligned
-// rows whatever P), + the harmonic tables on the last pass.
+// Shared memory: two load buffers + one work buffer of 2^k tables at a row stride of Ps = ffa_row_stride(P) counts, + the
+// harmonic tables on the last pass.
+// Last pass: Z^2_n of the 2^k final tables straight from shared memory.  tables x [1, cos_1, sin_1, ..] is a small dense
+// contraction (2^k x P x (1 + 2 nharm)), so for nharm <= 3 it runs on the FP64 tensor cores: one warp per 8 tables,
+// mma.sync.m8n8k4.f64 over the bins, the harmonic table pre-arranged in B-fragment order (first version: a warp per table
+// with three passes over the row and 50 shuffles -- 45 % of the last pass).
 // Fold step: 4 bins per lane and trip, all loads of a trip in flight before the first add, 32-bit shared-window
 // addresses.  (The first version -- one bin per lane and trip, generic pointers, a 64-bit modulo per table -- was bound by
 // instruction issue at 1 warp-instruction per bin and step; ncu history in DESIGN.md.)
 __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int P = a.P, k = a.k, s0 = a.s0;
-    const int Ps = (P + 3) & ~3, nvec = Ps >> 2;
+    const int Ps = ffa_row_stride(P), nvec = (P + 3) >> 2;
     const int nrow = 1 << k;
     const uint32_t tile_bytes = (uint32_t)nrow * (uint32_t)Ps * 4u;
     const uint32_t s_ld0 = smem_u32(smem_raw);  // load buffers: s_ld0, s_ld0 + tile_bytes; work buffer behind them
@@ -92,9 +104,27 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
     const long long ntiles = a.ntables >> k;
 
     const int step32 = 32 % P;  // rotated index advance between the 4 bins of a lane (32, or 32 mod P for tiny periods)
+    // bins covered by 4-bins-per-lane trips: a remainder of more than 64 bins still takes one (partly idle; its loads may
+    // run up to 96 words past the row, into the slack), a shorter one goes bin by bin
+    const int Pmain = (P & 127) > 64 ? ((P + 127) & ~127) : (P & ~127);
 
-    if (last)
+    // MMA epilogue: stab[kq][lane] = T[4 kq + lane % 4][lane / 4], T[j] = (1, cos_1 j, sin_1 j, cos_2 j, ...) padded with
+    // zeros to 8 columns and to a multiple of 4 bins; else the plain [2][nharm][P] tables
+    const bool mma_stat = last && a.nharm <= 3 && nrow >= 8;
+    if (mma_stat) {
+        const int nk = (P + 3) >> 2;
+        for (int i = threadIdx.x; i < nk * 32; i += blockDim.x) {
+            const int j = 4 * (i >> 5) + (i & 3), n = (i & 31) >> 2;
+            double v = 0.0;
+            if (j < P) {
+                if (n == 0) v = 1.0;
+                else if (n <= 2 * a.nharm) v = a.tab[(size_t)(((n - 1) & 1) * a.nharm + ((n - 1) >> 1)) * P + j];
+            }
+            stab[i] = v;
+        }
+    } else if (last) {
         for (int i = threadIdx.x; i < 2 * a.nharm * P; i += blockDim.x) stab[i] = a.tab[i];
+    }
 
     // gather of tile c: local table q <- table G + q*2^s0 + h; bins beyond the raw light curve are zero-filled by the
     // copy itself (src-size 0)
@@ -151,13 +181,13 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
                 // 4 bins per lane and trip at a lane stride of one word (bins j0, j0+32, j0+64, j0+96): every LDS / STS of
                 // the warp touches 32 consecutive words -- conflict-free.  (128-bit accesses for the unrotated table with
                 // four 16-byte-strided LDS.32 for the rotated one cost twice the wavefronts: 4-way bank conflicts, ncu.)
-                for (int j0 = lane; j0 < P; j0 += 128) {
+                for (int j0 = lane; j0 < Pmain; j0 += 128) {
                     int e = j0 + sh;
                     if (e >= P) e -= P;
                     uint32_t x[4], y[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        x[u] = lds_u32(a1 + (uint32_t)((j0 + 32 * u) << 2));  // may read up to 96 words past a short row: in-bounds
+                        x[u] = lds_u32(a1 + (uint32_t)((j0 + 32 * u) << 2));
                         y[u] = lds_u32(a2 + (uint32_t)(e << 2));
                         e += step32;
                         if (e >= P) e -= P;
@@ -165,6 +195,13 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
 #pragma unroll
                     for (int u = 0; u < 4; u++)
                         if (j0 + 32 * u < P) sts_u32(ao + (uint32_t)((j0 + 32 * u) << 2), x[u] + y[u]);
+                }
+                // the last P mod 128 bins, one per lane and trip (a 4-bin trip for them would be mostly idle lanes:
+                // P = 129 ran 55 % slower than P = 128 that way)
+                for (int j = Pmain + lane; j < P; j += 32) {
+                    int e = j + sh;
+                    if (e >= P) e -= P;
+                    sts_u32(ao + (uint32_t)(j << 2), lds_u32(a1 + (uint32_t)(j << 2)) + lds_u32(a2 + (uint32_t)(e << 2)));
                 }
             }
             __syncthreads();
@@ -176,18 +213,40 @@ __global__ void __launch_bounds__(512) ffa_pass_kernel(const FfaPassArgs a) {
 
         // s_in now holds tables c*2^k .. c*2^k + 2^k - 1 of the next level
         const uint32_t *in = reinterpret_cast<const uint32_t *>(smem_raw + (s_in - s_ld0));
-        if (last) {
+        if (mma_stat) {
+            const int nk = (P + 3) >> 2;
+            const int grp = lane >> 2, tig = lane & 3;
+            for (int r0 = warp * 8; r0 < nrow; r0 += nwarps * 8) {
+                const uint32_t arow = s_in + (uint32_t)(r0 + grp) * (uint32_t)Ps * 4u + (uint32_t)tig * 4u;
+                double d0 = 0.0, d1 = 0.0;  // D[grp][2 tig], D[grp][2 tig + 1]
+                for (int kq = 0; kq < nk; kq++) {
+                    // bins past P multiply zero table rows (the counts there are stale but finite)
+                    const double av = __uint2double_rn(lds_u32(arow + (uint32_t)kq * 16u));
+                    const double bv = stab[kq * 32 + lane];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(d0), "+d"(d1)
+                                 : "d"(av), "d"(bv));
+                }
+                // column 0 = total counts (lane tig 0, d0); every other column enters as its square
+                double sq = (tig == 0 ? 0.0 : d0 * d0) + d1 * d1;
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                const double tot = __shfl_sync(0xffffffffu, d0, lane & ~3);
+                if (tig == 0) a.stats[c * nrow + r0 + grp] = 2.0 / tot * sq;
+            }
+        } else if (last) {
             for (int r = warp; r < nrow; r += nwarps) {
                 const double z = ffa_row_stat(in + (size_t)r * Ps, P, a.nharm, stab, lane);
                 if (lane == 0) a.stats[c * nrow + r] = z;
             }
         } else {
             uint32_t *d = a.dst + (size_t)c * nrow * P;  // 2^k contiguous tables (row stride P in HBM)
-            if (a.vec4) {
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(in);
-                uint4 *d4 = reinterpret_cast<uint4 *>(d);
-                const int n4 = nrow * nvec;
-                for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = s4[i];
+            if (a.vec4) {  // P % 4 == 0: 128-bit copies, row by row (the shared-memory rows are padded)
+                for (int q = warp; q < nrow; q += nwarps) {
+                    const uint4 *s4 = reinterpret_cast<const uint4 *>(in + (size_t)q * Ps);
+                    uint4 *d4 = reinterpret_cast<uint4 *>(d + (size_t)q * P);
+                    for (int j4 = lane; j4 < nvec; j4 += 32) d4[j4] = s4[j4];
+                }
             } else {
                 for (int q = warp; q < nrow; q += nwarps)
                     for (int j = lane; j < P; j += 32) d[(size_t)q * P + j] = in[(size_t)q * Ps + j];
@@ -257,10 +316,10 @@ static int g_ffa_dev = -1, g_ffa_passes = 0, g_ffa_steps = 0, g_ffa_k = 0;
 static int g_ffa_k_override = 0;  // tuning hook: steps per pass (0: heuristic; -1: force the per-step HBM fallback)
 
 static size_t pass_smem(int k, int P, int nharm, bool last) {
-    // 2 load buffers + 1 work buffer at a row stride of ceil4(P) counts, 512 bytes of slack (the 4-bins-per-lane fold reads
-    // up to 96 words past a row whose length is not a multiple of 128; those values are never stored), the harmonic
-    // tables on the last pass
-    return (size_t)3 * ((size_t)1 << k) * ((P + 3) & ~3) * 4 + 512 + (last ? (size_t)2 * nharm * P * 8 : 0);
+    // 2 load buffers + 1 work buffer at a row stride of ceil4(P) counts (+ 512 bytes of slack), the harmonic tables on
+    // the last pass
+    return (size_t)3 * ((size_t)1 << k) * ffa_row_stride(P) * 4 + 512 +
+           (last ? std::max((size_t)2 * nharm * P * 8, (size_t)((P + 3) / 4) * 32 * 8) : 0);
 }
 
 int ffa_dev_impl(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, int nharm, const double *tab,
@@ -290,15 +349,16 @@ int ffa_dev_impl(const uint32_t *d_counts, int64_t n_raw, int64_t bin_period, in
     HX_CUDA_TRY(b_tab.alloc((size_t)2 * nharm * P * sizeof(double)));
     HX_CUDA_TRY(cudaMemcpyAsync(b_tab.p, tab, (size_t)2 * nharm * P * sizeof(double), cudaMemcpyHostToDevice, st));
 
-    // steps per pass: the largest k whose three buffers leave >= 2 CTAs per SM (measured on B200, tools/quick_ffa.py:
-    // fewer passes beat more resident CTAs up to there), else whatever fits
+    // steps per pass: as few passes over HBM as shared memory allows (k_fit steps fit in one CTA), split evenly -- measured
+    // on B200 (tools/quick_ffa.py): 3 passes of 7 steps at one 512-thread CTA per SM beat 4 passes of 5 at four CTAs per SM
     int k_fit = 0;
     for (int k = 1; k <= S && k <= 12; k++)
         if (pass_smem(k, P, nharm, true) <= (size_t)di.smem_optin) k_fit = k;
-    int k_pref = 0;
-    for (int k = 1; k <= k_fit; k++)
-        if (pass_smem(k, P, nharm, true) + di.reserved_smem <= (size_t)di.smem_per_sm / 2) k_pref = k;
-    if (k_pref < 3) k_pref = std::min(k_fit, 3);
+    int k_pref = k_fit;
+    if (k_fit > 0) {
+        const int npass_min = (S + k_fit - 1) / k_fit;
+        k_pref = (S + npass_min - 1) / npass_min;
+    }
     if (const char *e = getenv("HX_FFA_K")) g_ffa_k_override = atoi(e);
     int k_use = g_ffa_k_override > 0 ? std::min(g_ffa_k_override, k_fit) : k_pref;
     const bool fallback = g_ffa_k_override < 0 || k_use < 1;
