@@ -441,7 +441,7 @@ def run_ffa(args):
         ms = 0.0
         from hendrics_b200.ffa import _ffa_device
         for bp in range(int(np.floor(p0 / dt)), int(np.ceil(p1 / dt)) + 1):
-            _ffa_device(counts, bp)
+            _ffa_device(counts, bp, reuse_host_buffer=True)  # as ffa_search calls it
             k = _cabi.ffa_last_kernel()
             ms += k[0]
         kern.append((ms, k[1], k[2], k[3]))
