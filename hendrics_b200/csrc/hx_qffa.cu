@@ -917,9 +917,15 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     if (mode >= 1 && R == 4 && foot > 16) R = 2;
     int W = foot <= 16 ? 2 : 4;
     if (packed && foot == 64) R = 1, W = 2;  // nbin = 128 (the --fast default): many small CTAs, 16 resident warps
-    // batches of equal size (multiples of 32 centres), bounded by 512 MiB of profile scratch
+    // batches of equal size (multiples of 32 centres), bounded by 2 GiB of profile scratch (the whole C4 search -- 1252
+    // centres, 1.25 GB -- is one batch: 38.2 -> 36.2 ms per search against three 512 MiB batches, profiles/r01_sweep_qbatch.txt)
     const size_t per_centre = (size_t)nprof * nbin * 4;
-    const int64_t cap = std::max<int64_t>(32, (int64_t)(((size_t)512 << 20) / per_centre) / 32 * 32);
+    size_t batch_bytes = (size_t)2048 << 20;
+    if (const char *e = getenv("HX_QFFA_BATCH_MIB")) {  // tuning hook
+        const long long mib = atoll(e);
+        if (mib > 0) batch_bytes = (size_t)mib << 20;
+    }
+    const int64_t cap = std::max<int64_t>(32, (int64_t)(batch_bytes / per_centre) / 32 * 32);
     const int64_t n_batches = (n_centres + cap - 1) / cap;
     const int cb_max = (int)std::min<int64_t>(((n_centres + n_batches - 1) / n_batches + 31) / 32 * 32, n_centres + 31);
     const int slots_max = (cb_max + 31) / 32;
