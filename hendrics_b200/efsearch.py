@@ -38,7 +38,7 @@ from .base import (
     z2_n_detection_level,
 )
 from .io import HEN_FILE_EXTENSION, EFPeriodogram, get_file_type, load_folding, save_folding
-from .ffa import ffa_search
+from .ffa import ffa_search, h_test  # noqa: F401  (h_test is re-exported like hendrics/efsearch.py:46,85)
 from .search import epoch_folding_search, z_n_search
 
 log = logging.getLogger("hendrics_b200")
@@ -46,7 +46,7 @@ log = logging.getLogger("hendrics_b200")
 __all__ = [
     "folding_search", "search_with_qffa", "search_with_qffa_step", "check_phase_error_after_casting_to_double",
     "dyn_folding_search", "transient_search", "TransientResults", "analyze_qffa_results", "main_efsearch", "main_zsearch", "z_n_search",
-    "epoch_folding_search", "qffa_centres", "search_with_ffa",
+    "epoch_folding_search", "qffa_centres", "search_with_ffa", "h_test",
 ]
 
 

@@ -76,3 +76,22 @@ def test_ffa_tables_reproduce_the_arange_quirk():
     assert not np.allclose(tab[0, 1], np.cos(4 * np.pi * j / 49))  # the quirk
     tab = ho.ffa_tables(37, 2)
     np.testing.assert_allclose(tab[0, 1], np.cos(4 * np.pi * np.arange(37) / 37), atol=1e-14)
+
+
+def test_host_profile_helpers_known_answers():
+    """doctests of hendrics/ffa.py:126-131, 179-186, 200-206 on the host mirror (no GPU involved), and agreement with the
+    oracle's restatement on a random profile"""
+    from hendrics_b200.efsearch import h_test as h_test_reexported
+    from hendrics_b200.ffa import h_test, z_n_fast_cached, z_n_fast_cached_all
+
+    phase = 2 * np.pi * np.arange(0, 1, 0.01)
+    norm = np.sin(phase) + 1
+    assert np.isclose(z_n_fast_cached(norm, n=4), 50) and np.isclose(z_n_fast_cached(norm, n=2), 50)
+    ks, zs = z_n_fast_cached_all(norm, nmax=4)
+    assert ks[1] == 2 and np.isclose(zs[1], 50) and np.isclose(zs[3], 50)
+    h, m = h_test(norm, nmax=4)
+    assert np.isclose(h, 50) and m == 1 and h_test_reexported is h_test
+    prof = np.random.default_rng(3).poisson(30, 64).astype(float)
+    np.testing.assert_allclose(z_n_fast_cached(prof, 3), ho.z_n_fast_cached(prof, 3), rtol=1e-13)
+    np.testing.assert_allclose(z_n_fast_cached_all(prof, 5)[1], ho.z_n_fast_cached_all(prof, 5)[1], rtol=1e-13)
+    assert h_test(prof, nmax=5)[1] == ho.h_test(prof, nmax=5)[1]
