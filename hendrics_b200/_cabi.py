@@ -62,6 +62,7 @@ SIGNATURES = {
     "hx_fold_set_tuning": (_int, [_int, _int]),
     "hx_qffa_set_tuning": (_int, [_int]),
     "hx_fold_set_packing": (_int, [_int]),
+    "hx_fold_set_generic_fast": (_int, [_int]),
     "hx_wfold_set_tuning": (_int, [_int, _int, _int, _int]),
 }
 

@@ -35,6 +35,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "hx_common.cuh"
@@ -69,6 +70,7 @@ struct FoldArgs {
     long long n_tb_row;  // ROWFD: 32*R-trial blocks per fdot row (rows padded to a multiple of 32*R)
     int tile_ev;       // events per pipeline stage
     double scale;      // POW2: nbin*128, generic: 1
+    double gen_tmin;   // generic: events at t >= gen_tmin take the short exact path (phase >= 512 cycles); +inf: none
     double *stats;
     uint32_t *scratch;  // null => fused epilogue
     const double *tab;  // [2*nbin] cos, sin
@@ -107,7 +109,9 @@ __device__ __forceinline__ double exact_phase_frac(double t, double tt, double t
 // Returns the shared-memory word address of the bin; `inc` is the value to add (1 unless PACKED).
 // `m2` is the already rounded fdot term fl(tt*fdH) (computed once per event and thread when the R trials
 // of a thread share their fdot, ROWFD, else per trial).
-template <bool HAS_FD, int MODE>
+// GF (MODE_GENERIC only): the event has a phase of at least 512 cycles for every trial of the launch (t >= gen_tmin, decided
+// per stage) and takes the short exact path below.
+template <bool HAS_FD, int MODE, bool GF = false>
 __device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, double m2, double fN, double fdH,
                                              uint32_t mask, uint32_t topbit, int nbin, uint32_t cb, uint32_t &inc) {
     if (MODE == MODE_EXACT) {
@@ -127,6 +131,16 @@ __device__ __forceinline__ uint32_t bin_addr(double t, double tt, double tte, do
         if (MODE == MODE_PACKED) inc = (lo & topbit) | 1u;
         return (lo & mask) | cb;
     } else {
+        if (GF) {
+            // Any nbin, x >= 512 cycles.  The reference computes fr = x - floor(x) (exact) and floor(fl(fr * nbin)).  fr is a
+            // multiple of ulp(x) >= 2^-43 below 1, so fr * nbin (nbin < 2^10) has at most 53 significant bits: the product
+            // is exact and the reference's bin is floor(fr * nbin) = floor(x * nbin) - floor(x) * nbin in exact arithmetic.
+            // floor(x * nbin) is taken from the product rounded DOWN (rounding down never crosses an integer, integers
+            // being representable), so: 3 FP64 ops + 2 IMAD instead of 5 FP64 ops, no clamp needed (fr * nbin < nbin).
+            const uint32_t lp = (uint32_t)__double2loint(__dadd_rd(__dmul_rd(x, (double)nbin), HX_MAGIC));
+            const uint32_t lq = (uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC));
+            return cb + ((lp - lq * (uint32_t)nbin) << 7);  // mod 2^32 arithmetic; the true difference is in [0, nbin)
+        }
         double fl = __dsub_rn(__dadd_rd(x, HX_MAGIC), HX_MAGIC);  // floor(x), exact
         double fr = __dsub_rn(x, fl);                              // ph -= floor(ph)
         double z = __dmul_rn(fr, (double)nbin);
@@ -300,6 +314,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 
     const uint32_t mask = a.binmask, topbit = a.topbit;
     const int nbin = a.nbin;
+    const double gen_tmin = a.gen_tmin;
     const int nwarps = a.warps;
 
     // PACKED: drain this thread's packed words into the global scratch and clear them
@@ -336,6 +351,9 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
             __syncwarp();
         }
 
+        // the events of one stage; GF (generic mode only): every event of the stage takes the short exact path
+        auto run_stage = [&](auto gf_tag) {
+        constexpr bool GF = decltype(gf_tag)::value;
         int e = 0;
         EvGroup<HAS_FD, UE, EXACT> cur, nxt;
         if constexpr (SKEW) {
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         auto addr1 = [&](const EvGroup<HAS_FD, UE, EXACT> &g, int u, int r, uint32_t &inc) -> uint32_t {
             const int uu = HAS_FD ? u : 0;
             const double m2 = ROWFD ? g.m2[uu] : (HAS_FD ? __dmul_rn(g.tt[uu], fdH[r]) : 0.0);
-            return bin_addr<HAS_FD, MODE>(g.t[u], HAS_FD ? g.tt[uu] : 0.0, 0.0, m2, fN[r], fdH[r], mask, topbit, nbin,
+            return bin_addr<HAS_FD, MODE, GF>(g.t[u], HAS_FD ? g.tt[uu] : 0.0, 0.0, m2, fN[r], fdH[r], mask, topbit, nbin,
                                           cb[r], inc);
         };
         const int ngroups = cnt / UE;
@@ -401,7 +419,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
                     uint32_t inc;
                     const int uu = HAS_FD ? u : 0;
                     const double m2 = ROWFD ? cur.m2[uu] : (HAS_FD ? __dmul_rn(cur.tt[uu], fdH[r]) : 0.0);
-                    const uint32_t ad = bin_addr<HAS_FD, MODE>(cur.t[u], HAS_FD ? cur.tt[uu] : 0.0, (EXACT && HAS_FD) ? cur.tte[uu] : 0.0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                    const uint32_t ad = bin_addr<HAS_FD, MODE, GF>(cur.t[u], HAS_FD ? cur.tt[uu] : 0.0, (EXACT && HAS_FD) ? cur.tte[uu] : 0.0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                     if (PACKED) red_shared_add(ad, inc);
                     else red_shared_inc(ad);
                 }
@@ -421,10 +439,20 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
             for (int r = 0; r < R; r++) {
                 uint32_t inc;
                 const double m2 = HAS_FD ? __dmul_rn(tt0, ROWFD ? fdH_row : fdH[r]) : 0.0;
-                const uint32_t ad = bin_addr<HAS_FD, MODE>(t0, tt0, tte0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
+                const uint32_t ad = bin_addr<HAS_FD, MODE, GF>(t0, tt0, tte0, m2, fN[r], fdH[r], mask, topbit, nbin, cb[r], inc);
                 if (PACKED) red_shared_add(ad, inc);
                 else red_shared_inc(ad);
             }
+        }
+        };
+        if constexpr (MODE == MODE_GENERIC) {
+            // warp-uniform choice per stage: all its events late enough (phase >= 512 cycles for every trial)?
+            bool late = true;
+            for (int q = lane; q < cnt; q += 32) late &= *reinterpret_cast<const double *>(tp + (size_t)q * 8) >= gen_tmin;
+            if (__all_sync(0xffffffffu, late)) run_stage(std::true_type{});
+            else run_stage(std::false_type{});
+        } else {
+            run_stage(std::false_type{});
         }
         if (PACKED && ((it + 1) % a.flush_tiles == 0)) drain_packed();
         // stage hand-back without a block barrier: the last warp to finish `buf` refills it
@@ -627,6 +655,7 @@ static int g_fold_R_override = 0;  // testing/tuning hook (hx_fold_set_tuning)
 static int g_fold_W_override = 0;
 static int g_fold_pack_override = -1;  // -1 auto, 0 never, 1 whenever possible
 static int g_fold_m2t = 1;             // per-CTA fdot-term tile (M2T) when applicable; HX_FOLD_M2T=0 disables it
+static int g_fold_gen_fast = 1;        // short exact path of the generic mode (hx_fold_set_generic_fast)
 
 // min/max of the event times, trial frequencies and fdots (device arrays): out = [tmin,tmax, fmin,fmax, fdmin,fdmax];
 // fails with HX_ERR_ARG when any of them is not finite.  Synchronizes `st`.
@@ -848,6 +877,16 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     // the low field of a packed word holds 2^pack_shift - 1 events before it carries
     a.flush_tiles = std::max(1, (int)(((1u << a.pack_shift) - 1u) / (uint32_t)best.tile_ev));
     a.scale = (mode == MODE_POW2 || mode == MODE_PACKED) ? (double)nbin * 128.0 : 1.0;
+    // generic mode, short exact path: needs non-negative phases, phase * nbin inside the magic-add range, and a phase of
+    // at least 512 cycles, which holds for every trial once t * (fmin + t * min(fdmin, 0) / 2) >= 512; the bound below is
+    // evaluated with a safety margin (events it excludes just take the reference's operation sequence)
+    a.gen_tmin = INFINITY;
+    if (mode == MODE_GENERIC && nonneg && !(flags & HX_FOLD_FORCE_GENERIC) && phmax * nbin < 1125899906842624.0 /* 2^50 */ &&
+        fmin > 0) {
+        const double feff = fmin + 0.5 * tmax * std::min(fdmin, 0.0);  // smallest f + t*fd/2 over the data span
+        if (feff > 0) a.gen_tmin = 512.0 / feff * (1.0 + 1e-9) + 1e-9;
+    }
+    if (g_fold_gen_fast == 0) a.gen_tmin = INFINITY;
     a.stats = d_stats, a.scratch = reinterpret_cast<uint32_t *>(d_scratch), a.tab = reinterpret_cast<double *>(d_tab);
     a.warps = W, a.hist_off = best.hist_off, a.tile_off = best.tile_off, a.ev_per_split = ev_per_split;
     a.errflag = d_err;
@@ -935,6 +974,11 @@ int hx_fold_last_kernel_shape(int *R, int *mode, int *rowfd, int *m2t, double *f
     }
     if (smem_wavefronts_per_unit)  // one ATOMS per unit; a broadcast fp64 costs one wavefront per event and warp (LDS.128 = 2 events)
         *smem_wavefronts_per_unit = 1.0 + (hx::g_last_m2t ? 2.0 : 1.0) / r;
+    return HX_OK;
+}
+
+int hx_fold_set_generic_fast(int on) {
+    hx::g_fold_gen_fast = on ? 1 : 0;
     return HX_OK;
 }
 

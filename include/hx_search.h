@@ -244,6 +244,7 @@ int hx_qffa_set_tuning(int centres_per_pass);
  * bit 2: never drop zero-weight entries */
 int hx_wfold_set_tuning(int trials_per_thread, int events_per_group, int warps_per_cta, int force_generic);
 int hx_fold_set_packing(int mode); /* 0: never pack counters, 1: whenever possible, other: automatic */
+int hx_fold_set_generic_fast(int on); /* 0: non power-of-two nbin always replays the reference's operation sequence */
 
 #ifdef __cplusplus
 }

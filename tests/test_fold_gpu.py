@@ -355,3 +355,31 @@ def test_concurrent_calls_from_host_threads():
     assert not errs
     for k in range(4):
         assert np.array_equal(out[k], want_z if k % 2 else want_e)
+
+
+@pytest.mark.parametrize("nbin,fdots,f_lo", [(20, [0.0], 9.8), (100, [0.0, -3e-6, 2e-6], 9.8), (1000, [0.0], 0.7), (24, [-1e-7], 150.0)])
+def test_generic_short_path_equals_reference_sequence_and_oracle(nbin, fdots, f_lo):
+    """Non power-of-two nbin: the short exact path (phase >= 512 cycles: floor(x*nbin) - floor(x)*nbin from a rounded-down
+    product) gives the reference's bins -- compared with the operation-by-operation replay (hx_fold_set_generic_fast(0)) and
+    with the oracle; events below and above the 512-cycle threshold, unsorted events (mixed stages), negative fdot."""
+    from hendrics_b200 import _cabi
+
+    rng = np.random.default_rng(nbin)
+    ts = np.sort(rng.uniform(0.0, 3000.0, 40000))
+    ts[:50] = rng.uniform(0.0, 512.5 / f_lo, 50)  # around the threshold t = 512 / f
+    ts[5000:5010] = 512.0 / (f_lo + 0.01 * np.arange(10))  # phases of ~512 cycles exactly
+    rng.shuffle(ts[10000:20000])  # unsorted part: stages mixing early and late events
+    freqs = f_lo + 0.2 * np.arange(70) / 70
+    lib = _cabi.lib()
+    try:
+        lib.hx_fold_set_generic_fast(1)
+        s_fast, p_fast = _host_call(ts, freqs, fdots, nbin, 2)
+        lib.hx_fold_set_generic_fast(0)
+        s_ref, p_ref = _host_call(ts, freqs, fdots, nbin, 2)
+    finally:
+        lib.hx_fold_set_generic_fast(1)
+    assert np.array_equal(p_fast, p_ref)
+    assert np.array_equal(s_fast, s_ref)
+    o_s, o_p = C.fold_search(ts, freqs, fdots, nbin, 2, want_profiles=True)
+    assert np.array_equal(p_fast.astype(np.int64), o_p)
+    _assert_stats(s_fast, o_s)
