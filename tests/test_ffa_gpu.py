@@ -159,3 +159,28 @@ def test_ffa_large_light_curve_conserves_counts_and_matches_fold():
     prof = np.zeros(P)
     np.add.at(prof, t % P, counts)
     np.testing.assert_allclose(st[0], ho.z_n_fast_cached(prof, 2), rtol=RTOL)
+
+
+def test_ffa_randomized_periods_lengths_and_pass_splits():
+    """random bin periods (aligned / unaligned, tiny, > 128), ragged light-curve lengths, random steps-per-pass overrides,
+    nharm 1..4 (tensor-core epilogue for <= 3, plain epilogue for 4): always the oracle's numbers"""
+    from hendrics_b200 import _cabi
+    from hendrics_b200.ffa import ffa
+    from oracle import hx_oracle as ho
+
+    rng = np.random.default_rng(2024)
+    lib = _cabi.lib()
+    for trial in range(24):
+        P = int(rng.choice([2, 3, 5, 8, 17, 31, 32, 33, 64, 100, 127, 128, 129, 130, 131, 200, 257, 300]))
+        ntab_target = int(2 ** rng.integers(1, 11))
+        n_raw = int(P * ntab_target - rng.integers(0, P))
+        counts = rng.poisson(rng.choice([0.05, 1.0, 20.0]), max(n_raw, P + 1)).astype(np.float64)
+        z_n_n = int(rng.integers(1, 5))
+        lib.hx_ffa_set_tuning(int(rng.choice([0, 1, 2, 3, 4, 5, 6, 8, -1])))
+        per, st = ffa(counts, P, z_n_n=z_n_n)
+        per_o, st_o = ho.ffa(counts, P, z_n_n=z_n_n)
+        assert np.array_equal(per, per_o), (trial, P)
+        # rtol 1e-9; atol 1e-9 for statistics that cancel to ~0 (e.g. two equal bins at P = 2: c_1 = k - k)
+        assert np.array_equal(np.isnan(st), np.isnan(st_o)), (trial, P)
+        ok = ~np.isnan(st_o)
+        np.testing.assert_allclose(st[ok], st_o[ok], rtol=RTOL, atol=1e-9, err_msg=f"trial {trial} P={P} n={z_n_n}")
