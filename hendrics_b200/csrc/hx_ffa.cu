@@ -14,7 +14,8 @@
 // shift increased by h*2^sigma.  So one CTA gathers its 2^k tables into shared memory (coalesced row reads, zero beyond the
 // raw light curve: the padded copy is never materialised), runs k steps between two shared-memory buffers and writes 2^k
 // contiguous tables -- or, on the last pass, only their Z^2_n: the final tables never reach HBM.  HBM traffic is
-// 8 B per table element and PASS instead of per step (log2(ntables) = 20, k = 5: 4 passes).
+// 8 B per table element and PASS instead of per step (log2(ntables) = 20: 3 passes of 7, 7, 6 steps).  Within a step a warp
+// folds output tables 2m and 2m+1 together: they read the same two input tables with shifts one bin apart.
 // Counts are uint32: the reference adds integer-valued doubles, which is exact, so integer sums are the same numbers.
 #include <algorithm>
 #include <cmath>
