@@ -77,7 +77,7 @@ __device__ __forceinline__ double ffa_row_stat(const uint32_t *row, int P, int n
         c = warp_sum(c), s = warp_sum(s);
         res += c * c + s * s;
     }
-    return 2.0 / tot * res;  // an all-zero (padding) table gives inf * 0 = NaN, like the reference
+    return 2.0 / tot * res;  // tot = all the counts of the light curve; an empty one gives inf * 0 = NaN
 }
 
 // Persistent CTAs: tile t+1 (the 2^k tables of the next working set) is prefetched with asynchronous copies (LDGSTS)

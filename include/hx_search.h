@@ -182,7 +182,7 @@ int hx_topk_dev(const double *d_stats, int64_t n, int k, int64_t *h_idx, double 
  * hx_ffa[_dev] replaces `ffa` / `_ffa` / `ffa_step` (hendrics/ffa.py:291-349): the light curve counts[n_raw] is
  * zero-padded to ntables x bin_period (ntables = 2^ceil(log2(n_raw / bin_period + 1)), computed by the caller like
  * ffa.py:340), folded in log2(ntables) steps and stats[i] = Z^2_nharm of table i (trial period bin_period +
- * i / (ntables - 1) bins); all-zero tables give NaN like the reference.  tab is a HOST array [2][nharm][bin_period]:
+ * i / (ntables - 1) bins); an empty light curve gives NaN (the reference's numba code raises ZeroDivisionError).  tab is a HOST array [2][nharm][bin_period]:
  * the cos (tab[0]) and sin (tab[1]) value harmonic h+1 multiplies bin j with, i.e. the stride-(h+1) slices of the
  * reference's tiled tables (ffa.py:98-102, 320-328; the caller builds them with numpy exactly as the reference does,
  * including the off-by-one length of np.arange(0, 1, 1/bin_period) for some periods).  Counts are uint32 (the

@@ -168,13 +168,15 @@ def test_ffa_randomized_periods_lengths_and_pass_splits():
     from hendrics_b200.ffa import ffa
     from oracle import hx_oracle as ho
 
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(int(os.environ.get("HX_TEST_SEED", 2024)))
     lib = _cabi.lib()
     for trial in range(24):
         P = int(rng.choice([2, 3, 5, 8, 17, 31, 32, 33, 64, 100, 127, 128, 129, 130, 131, 200, 257, 300]))
         ntab_target = int(2 ** rng.integers(1, 11))
         n_raw = int(P * ntab_target - rng.integers(0, P))
         counts = rng.poisson(rng.choice([0.05, 1.0, 20.0]), max(n_raw, P + 1)).astype(np.float64)
+        if counts.sum() == 0:  # every final table holds ALL the counts: an empty light curve divides by zero (the
+            counts[0] = 1.0    # reference's numba code raises ZeroDivisionError there, hx_ffa returns NaN)
         z_n_n = int(rng.integers(1, 5))
         lib.hx_ffa_set_tuning(int(rng.choice([0, 1, 2, 3, 4, 5, 6, 8, -1])))
         per, st = ffa(counts, P, z_n_n=z_n_n)
