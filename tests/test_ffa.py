@@ -95,3 +95,17 @@ def test_host_profile_helpers_known_answers():
     np.testing.assert_allclose(z_n_fast_cached(prof, 3), ho.z_n_fast_cached(prof, 3), rtol=1e-13)
     np.testing.assert_allclose(z_n_fast_cached_all(prof, 5)[1], ho.z_n_fast_cached_all(prof, 5)[1], rtol=1e-13)
     assert h_test(prof, nmax=5)[1] == ho.h_test(prof, nmax=5)[1]
+
+
+def test_host_tables_and_period_grid_match_the_oracle():
+    """host-side pieces of hendrics_b200.ffa that need no GPU: the harmonic tables handed to hx_ffa (including the periods
+    where np.arange overshoots) and the trial-period grid of hendrics/ffa.py:314"""
+    from hendrics_b200.ffa import _ffa_tables, _period_fractions
+
+    for bp in (2, 16, 37, 49, 98, 103, 128, 250):
+        for n in (1, 2, 4):
+            assert np.array_equal(_ffa_tables(bp, n), ho.ffa_tables(bp, n)), (bp, n)
+    for ntab in (2, 8, 1024):
+        ref = np.array([5 + n / (ntab - 1) for n in range(ntab)])
+        assert np.array_equal(5 + _period_fractions(ntab), ref)
+        assert not _period_fractions(ntab).flags.writeable  # cached: must not be modified in place
