@@ -109,3 +109,41 @@ def test_host_tables_and_period_grid_match_the_oracle():
         ref = np.array([5 + n / (ntab - 1) for n in range(ntab)])
         assert np.array_equal(5 + _period_fractions(ntab), ref)
         assert not _period_fractions(ntab).flags.writeable  # cached: must not be modified in place
+
+
+def test_ffa_oracle_properties():
+    """size-independent properties of the fast folding algorithm (the same ones tests/test_ffa_gpu.py uses at scale):
+    table 0 is the plain fold at P bins, every table keeps all the counts, the last table of bin period P is the
+    zero-drift table of P + 1 folded from the same data, and the search grid is increasing within a bin period"""
+    rng = np.random.default_rng(12)
+    P, n_raw = 24, 24 * 200 + 7
+    counts = rng.poisson(3.0, n_raw).astype(np.float64)
+    ntab = int(2 ** np.ceil(np.log2(n_raw // P + 1)))
+    arr = np.zeros(ntab * P)
+    arr[:n_raw] = counts
+    arr = arr.reshape(ntab, P)
+    for step in range(int(np.log2(ntab))):
+        arr = ho.ffa_step(arr, step, ntab)
+    assert np.all(arr.sum(axis=1) == counts.sum())          # every table holds all the counts
+    prof = np.zeros(P)
+    np.add.at(prof, np.arange(n_raw) % P, counts)
+    assert np.array_equal(arr[0], prof)                      # no drift: the plain fold
+    # maximal drift: one bin per table row, i.e. row r is rolled by -r -> folding at P + 1 bins, seen modulo P
+    prof1 = np.zeros(P)
+    idx = np.arange(ntab * P)
+    row, col = idx // P, idx % P
+    padded = np.zeros(ntab * P)
+    padded[:n_raw] = counts
+    np.add.at(prof1, (col - row) % P, padded)
+    assert np.array_equal(arr[ntab - 1], prof1)
+    per, st = ho.ffa(counts, P)
+    assert per[0] == P and per[-1] == P + 1 and np.all(np.diff(per) > 0)
+    np.testing.assert_allclose(st[0], ho.z_n_fast_cached(prof, 2), rtol=1e-12)
+    # linearity of the tables in the light curve
+    c2 = rng.poisson(1.0, n_raw).astype(np.float64)
+    a1 = np.zeros(ntab * P); a1[:n_raw] = c2; a1 = a1.reshape(ntab, P)
+    a12 = np.zeros(ntab * P); a12[:n_raw] = counts + c2; a12 = a12.reshape(ntab, P)
+    for step in range(int(np.log2(ntab))):
+        a1 = ho.ffa_step(a1, step, ntab)
+        a12 = ho.ffa_step(a12, step, ntab)
+    assert np.array_equal(a12, arr + a1)
