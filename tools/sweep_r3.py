@@ -1,4 +1,7 @@
-"""(R, W) sweep of the (f, fdot) kernel including 3 trials per thread, nbin = 32 / 64 / 128; statistics checked against the first combo."""
+"""(R, W) sweep of the (f, fdot) kernel, nbin = 32 / 64 / 128; statistics checked against the first combo.
+
+Written for the 3-trials-per-thread experiment (profiles/r01_sweep_r3.txt): the R = 3 instantiations were removed again
+(never better than R = 2), so `hx_fold_set_tuning(3, W)` now means "default R"; R = 2 / 4 / 8 combinations still sweep."""
 import os, sys, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
