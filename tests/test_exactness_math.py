@@ -1,0 +1,96 @@
+"""CPU checks of the exactness arguments the CUDA kernels rely on, independent of any GPU run.
+
+np.longdouble (x87, 64-bit mantissa on this platform) holds x * nbin exactly for a 53-bit x and nbin < 2^10, so it serves
+as exact arithmetic here; the reference's own operation sequence is evaluated in float64 as numpy does.
+"""
+import numpy as np
+import pytest
+
+LD_OK = np.finfo(np.longdouble).nmant >= 63
+
+
+def _reference_bins(x, nbin):
+    """_pulse_phase_fast / _profile_fast on an already computed phase x: ph - floor(ph), floor(ph * nbin), A4 clamp"""
+    fr = x - np.floor(x)
+    return np.minimum(np.floor(fr * nbin).astype(np.int64), nbin - 1)
+
+
+def _adversarial_phases(rng, nbin, lo, hi, n):
+    """phases in [lo, hi): random ones plus values a few ulps around every kind of bin edge"""
+    x = rng.uniform(lo, hi, n)
+    k = np.floor(rng.uniform(lo, hi - 1, n))
+    j = rng.integers(0, nbin + 1, n)
+    edge = k + j / nbin
+    for d in (-3, -2, -1, 0, 1, 2, 3):
+        y = edge.copy()
+        for _ in range(abs(d)):
+            y = np.nextafter(y, np.inf if d > 0 else -np.inf)
+        x = np.concatenate([x, y])
+    return x[(x >= lo) & (x < hi)]
+
+
+@pytest.mark.skipif(not LD_OK, reason="needs an 80-bit long double as exact arithmetic")
+@pytest.mark.parametrize("nbin", [3, 7, 10, 20, 24, 48, 50, 100, 777, 1000, 1023])
+def test_generic_short_path_identity(nbin):
+    """x >= 512: the reference's bin equals floor(x * nbin) - floor(x) * nbin in exact arithmetic, and the product rounded
+    DOWN to fp64 has the same floor (what hx_fold.cu's GF path computes with DMUL.RD + two magic adds + IMAD)."""
+    rng = np.random.default_rng(nbin)
+    for lo, hi in ((512.0, 1024.0), (1e4, 1e5), (3e6, 4e6), (1e9, 2e9), (2.0**40, 2.0**40 + 1e6)):
+        x = _adversarial_phases(rng, nbin, lo, hi, 20000)
+        ref = _reference_bins(x, nbin)
+        p = x.astype(np.longdouble) * np.longdouble(nbin)  # exact
+        assert np.all(p.astype(np.float64).astype(np.longdouble) - p <= np.spacing(p.astype(np.float64)))  # sanity
+        exact = (np.floor(p) - np.floor(x).astype(np.longdouble) * nbin).astype(np.int64)
+        assert np.array_equal(exact, ref), (nbin, lo)
+        # fp64 product rounded down: the largest double <= p
+        pr = p.astype(np.float64)
+        pr = np.where(pr.astype(np.longdouble) > p, np.nextafter(pr, -np.inf), pr)
+        assert np.all(pr.astype(np.longdouble) <= p)
+        assert np.array_equal(np.floor(pr), np.floor(p).astype(np.float64)), (nbin, lo)
+
+
+def test_generic_short_path_needs_the_512_cycle_threshold():
+    """below 512 cycles fr * nbin is not always exact: there the rounded product can reach the next integer (the reference
+    then bins one higher than exact arithmetic), which is why those events replay the reference's operation sequence"""
+    if not LD_OK:
+        pytest.skip("needs an 80-bit long double")
+    found = False
+    rng = np.random.default_rng(5)
+    for nbin in (3, 7, 10, 20, 100, 777, 1000):
+        x = _adversarial_phases(rng, nbin, 0.0, 8.0, 200000)
+        ref = _reference_bins(x, nbin)
+        p = x.astype(np.longdouble) * np.longdouble(nbin)
+        exact = (np.floor(p) - np.floor(x).astype(np.longdouble) * nbin).astype(np.int64)
+        found |= bool(np.any(exact != ref))
+    assert found
+
+
+@pytest.mark.parametrize("nbin", [2, 16, 128, 256])
+def test_power_of_two_fast_path_identity(nbin):
+    """power-of-two nbin, x >= 0: scaling by nbin * 128 is exact, so the low bits of floor(x * nbin * 128) hold the
+    reference's bin (bits [7, 7 + log2 nbin)) -- the magic-add / AND path of K1 and K2."""
+    rng = np.random.default_rng(nbin)
+    for lo, hi in ((0.0, 4.0), (1.0, 1e3), (1e6, 2e6), (1e9, 1e9 + 1e5)):
+        x = _adversarial_phases(rng, nbin, lo, hi, 20000)
+        ref = _reference_bins(x, nbin)
+        scaled = x * (nbin * 128.0)  # exact (power of two)
+        fast = (np.floor(scaled).astype(np.int64) >> 7) & (nbin - 1)
+        assert np.array_equal(fast, ref), (nbin, lo)
+
+
+def test_packed_counter_increment_encoding():
+    """nbin >= 128 packed counters: word = bin mod nbin/2, increment (lo & topbit) | 1 puts upper-half bins in the high
+    field; unpacking low - high / high recovers both bins for any event sequence shorter than the flush interval"""
+    nbin, log2 = 128, 7
+    shift = 6 + log2
+    topbit = 1 << shift
+    rng = np.random.default_rng(0)
+    bins = rng.integers(0, nbin, 8000)  # < 2^shift - 1 events
+    words = np.zeros(nbin // 2, dtype=np.int64)
+    for b in bins:
+        lo = int(b) << 7  # the scaled phase's low word: bin at bits [7, 14)
+        words[(lo >> 7) & (nbin // 2 - 1)] += (lo & topbit) | 1
+    up = words >> shift
+    low = (words & (topbit - 1)) - up
+    ref = np.bincount(bins, minlength=nbin)
+    assert np.array_equal(np.concatenate([low, up]), ref)
