@@ -94,3 +94,21 @@ def test_packed_counter_increment_encoding():
     low = (words & (topbit - 1)) - up
     ref = np.bincount(bins, minlength=nbin)
     assert np.array_equal(np.concatenate([low, up]), ref)
+
+
+@pytest.mark.skipif(not LD_OK, reason="needs an 80-bit long double as exact arithmetic")
+def test_phase_fraction_is_exact_outside_minus_half_to_zero():
+    """`ph - floor(ph)` is computed without rounding for ph >= 0 and for ph <= -0.5 (K1's non-negative fast path, K2's
+    |ph| >= 0.75 condition); inside (-0.5, 0) it can round, which is why those photons replay the reference's sequence
+    (K1 generic mode, K2's fix-up kernel)."""
+    rng = np.random.default_rng(1)
+    mags = np.concatenate([rng.uniform(0.5, 4, 100000), 10 ** rng.uniform(0, 9, 100000)])
+    for sign in (1.0, -1.0):
+        ph = sign * mags
+        fr = ph - np.floor(ph)
+        exact = ph.astype(np.longdouble) - np.floor(ph).astype(np.longdouble)
+        assert np.array_equal(fr.astype(np.longdouble), exact)
+    ph = -rng.uniform(1e-9, 0.5, 200000)
+    fr = ph - np.floor(ph)
+    exact = ph.astype(np.longdouble) - np.floor(ph).astype(np.longdouble)
+    assert np.any(fr.astype(np.longdouble) != exact)
