@@ -147,3 +147,52 @@ def test_ffa_oracle_properties():
         a1 = ho.ffa_step(a1, step, ntab)
         a12 = ho.ffa_step(a12, step, ntab)
     assert np.array_equal(a12, arr + a1)
+
+
+def _blocked_ffa(counts, P, ks):
+    """numpy restatement of csrc/hx_ffa.cu's index arithmetic: passes of k fused steps on gathered working sets, the shift
+    offset hs = (h * 2^sigma) mod P doubled from step to step, output tables folded in pairs (2m, 2m+1 share both inputs,
+    shifts one bin apart)."""
+    n_raw = len(counts)
+    ntables = int(2 ** np.ceil(np.log2(n_raw // P + 1)))
+    A = np.zeros(ntables * P, dtype=np.int64)
+    A[:n_raw] = counts
+    A = A.reshape(ntables, P)
+    assert sum(ks) == int(np.log2(ntables))
+    s0 = 0
+    for k in ks:
+        out = np.zeros_like(A)
+        for c in range(ntables >> k):
+            h = c & ((1 << s0) - 1)
+            G = (c >> s0) << (s0 + k)
+            B = np.stack([A[G + (q << s0) + h] for q in range(1 << k)])
+            hs = h % P
+            for sg in range(k):
+                B2 = np.zeros_like(B)
+                for r in range(0, 1 << k, 2):
+                    mu = r & ((2 << sg) - 1)
+                    i1 = (r - mu) + (mu >> 1)
+                    i2 = i1 + (1 << sg)
+                    sh = (hs + (mu >> 1)) % P
+                    B2[r] = B[i1] + np.roll(B[i2], -sh)
+                    B2[r + 1] = B[i1] + np.roll(B[i2], -(sh + 1))
+                B = B2
+                hs = (2 * hs) % P
+            out[c << k:(c + 1) << k] = B
+        A = out
+        s0 += k
+    return A
+
+
+@pytest.mark.parametrize("P,n_raw,ks", [(7, 7 * 60 + 3, (2, 2, 2)), (16, 16 * 200 + 5, (3, 3, 2)), (5, 5 * 31 + 1, (1, 4)),
+                                        (5, 5 * 31 + 1, (5,)), (9, 9 * 100, (4, 3)), (3, 3 * 500, (1,) * 9), (129, 129 * 60, (3, 3))])
+def test_blocked_pairwise_butterfly_equals_the_reference_steps(P, n_raw, ks):
+    rng = np.random.default_rng(P)
+    counts = rng.poisson(3.0, n_raw)
+    ntables = int(2 ** np.ceil(np.log2(n_raw // P + 1)))
+    arr = np.zeros(ntables * P)
+    arr[:n_raw] = counts
+    arr = arr.reshape(ntables, P)
+    for step in range(int(np.log2(ntables))):
+        arr = ho.ffa_step(arr, step, ntables)
+    assert np.array_equal(_blocked_ffa(counts, P, ks), arr.astype(np.int64))
