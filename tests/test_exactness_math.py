@@ -112,3 +112,45 @@ def test_phase_fraction_is_exact_outside_minus_half_to_zero():
     fr = ph - np.floor(ph)
     exact = ph.astype(np.longdouble) - np.floor(ph).astype(np.longdouble)
     assert np.any(fr.astype(np.longdouble) != exact)
+
+
+def test_fdot_term_operand_orders_round_identically():
+    """A3 / K1: the reference's ((0.5 * t) * t) * fd, the kernel's fl(t * t) * (0.5 * fd) and the pre-scaled
+    fl(t * t) * (0.5 * fd * nbin * 128) / (nbin * 128) are the same double: scaling by powers of two commutes with rounding
+    (no underflow in the ranges the host admits)."""
+    rng = np.random.default_rng(3)
+    t = np.concatenate([rng.uniform(0, 1e5, 200000), 10 ** rng.uniform(-3, 8.5, 200000)])
+    fd = np.concatenate([rng.uniform(-1, 1, 200000) * 10 ** rng.uniform(-15, -4, 200000)] * 2)
+    ref = ((0.5 * t) * t) * fd
+    assert np.array_equal((t * t) * (0.5 * fd), ref)
+    for nbin in (16, 128, 1024):
+        s = nbin * 128.0
+        assert np.array_equal(((t * t) * ((0.5 * fd) * s)) / s, ref)
+        # and the scaled sum: fl(t*f*s) + fl(m2*s) rounds like (fl(t*f) + fl(m2)) * s
+        f = rng.uniform(0.01, 1000, t.size)
+        assert np.array_equal((t * (f * s)) + ((t * t) * ((0.5 * fd) * s)), ((t * f) + ref) * s)
+
+
+def test_harmonic_domain_shift_and_sum_identity():
+    """K3: a circular shift of a profile rotates its k-th harmonic by k * theta_shift, so the Z^2_n of the shifted sum of
+    the time slices is obtained from per-slice harmonic coefficients (what qffa_step2_kernel accumulates) -- equal to the
+    direct roll-and-add of hendrics/efsearch.py:350-363 to rounding."""
+    rng = np.random.default_rng(4)
+    nprof, nbin, n = 32, 64, 3
+    prof = rng.poisson(5.0, (nprof, nbin)).astype(np.float64)
+    shifts = rng.integers(0, nbin, nprof)
+    splat = np.zeros(nbin)
+    for k in range(nprof):
+        splat += np.roll(prof[k], shifts[k])
+    j = np.arange(nbin)
+    direct = 0.0
+    viaco = 0.0
+    for h in range(1, n + 1):
+        c, s = np.cos(2 * np.pi * h * j / nbin), np.sin(2 * np.pi * h * j / nbin)
+        direct += (splat @ c) ** 2 + (splat @ s) ** 2
+        Cr, Sr = prof @ c, prof @ s                      # per-slice coefficients
+        th = 2 * np.pi * h * shifts / nbin
+        C = np.sum(Cr * np.cos(th) - Sr * np.sin(th))    # roll by +s: bin b <- b - s, phase advances by theta_s
+        S = np.sum(Sr * np.cos(th) + Cr * np.sin(th))
+        viaco += C ** 2 + S ** 2
+    np.testing.assert_allclose(viaco, direct, rtol=1e-12)
