@@ -42,7 +42,7 @@ SIGNATURES = {
                               _c_u32p, _int]),
     "hx_qffa_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _c_dp, _i64, _int, _int, _c_dp, _c_dp, _i64,
                                   _int, _vp, _vp, _vp]),
-    "hx_transient_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _i64, _int, _int, _int, _int, _vp, _vp]),
+    "hx_transient_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _c_dp, _c_dp, _i64, _int, _int, _int, _int, _int, _vp, _vp]),
     "hx_orbital_search": (_int, [_c_dp, _i64, _dbl, _dbl, _dbl, _dbl, _c_dp, _i64, _int, _int, _c_dp, _c_u32p, _int]),
     "hx_orbital_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _dbl, _dbl, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "hx_zn_unbinned": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _c_dp, _int]),
@@ -113,8 +113,6 @@ def check(rc):
         msg = lib().hx_last_error().decode("utf-8", "replace")
         if rc == HX_ERR_RANGE:
             raise HxRangeError(rc, msg)
-        if rc == HX_ERR_ARG:
-            raise HxError(rc, msg)
         raise HxError(rc, msg)
 
 

@@ -100,8 +100,12 @@ def _gpu_topk(flat, n):
     idx = np.empty(n, dtype=np.int64)
     val = np.empty(n, dtype=np.float64)
     n_out = ctypes.c_int64(0)
+    import torch
+
+    # the caller's CURRENT device (one rank per GPU: never cuda:0 by default); the entry point restores it on return
+    device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     rc = _cabi.lib().hx_topk(_cabi.dptr(flat), flat.size, int(n), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                             _cabi.dptr(val), ctypes.byref(n_out), 0)
+                             _cabi.dptr(val), ctypes.byref(n_out), int(device))
     _cabi.check(rc)
     return idx[: n_out.value]
 

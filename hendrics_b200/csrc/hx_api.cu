@@ -44,19 +44,20 @@ int get_device_info(int device, DeviceInfo *out) {
     std::lock_guard<std::mutex> lk(g_info_mu);
     if (!g_info_ok[device]) {
         DeviceInfo di{};
-        int major = 0;
+        int major = 0, minor = 0;
         HX_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
-        if (major < 10) {
-            set_error("device %d has compute capability %d.x; libhxsearch is built for sm_100a only", device, major);
+        HX_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        if (major != 10) {  // the library holds one sm_100a cubin: arch-specific code runs on compute capability 10.x only
+            set_error("device %d has compute capability %d.%d; libhxsearch is built for sm_100a (B200) only", device, major,
+                      minor);
             return HX_ERR_CUDA;
         }
         HX_CUDA_TRY(cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, device));
         HX_CUDA_TRY(cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         HX_CUDA_TRY(cudaDeviceGetAttribute(&di.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
         HX_CUDA_TRY(cudaDeviceGetAttribute(&di.reserved_smem, cudaDevAttrReservedSharedMemoryPerBlock, device));
-        int cur = 0;
-        HX_CUDA_TRY(cudaGetDevice(&cur));
-        HX_CUDA_TRY(cudaSetDevice(device));
+        DeviceGuard guard;  // back on the caller's device on every exit path below
+        HX_CUDA_TRY(guard.enter(device));
         {
             // keep stream-ordered temporaries (cudaMallocAsync) cached across calls: by default the
             // pool hands memory back to the OS at every synchronisation point
@@ -72,9 +73,11 @@ int get_device_info(int device, DeviceInfo *out) {
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpy(&di.dyn_smem_base, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
         cudaFree(d);
-        cudaSetDevice(cur);
         if (e != cudaSuccess) {
-            set_error("probe_smem_base_kernel failed: %s", cudaGetErrorString(e));
+            if (e == cudaErrorNoKernelImageForDevice)
+                set_error("device %d (compute capability %d.%d) cannot run this library's sm_100a kernels", device, major, minor);
+            else
+                set_error("probe_smem_base_kernel failed: %s", cudaGetErrorString(e));
             return HX_ERR_CUDA;
         }
         count_launch();

@@ -40,6 +40,24 @@ std::recursive_mutex &api_mutex();
         hx::count_launch();                                                            \
     } while (0)
 
+// Host-pointer entry points run on the device they are given and put the calling thread back on the device it
+// was on, on every exit path (a multi-GPU process keeps one current device per rank: it must not be moved to cuda:0
+// behind torch's / NCCL's back).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t enter(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) {
+            prev = -1;
+            return e;
+        }
+        return cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 // RAII device buffer for the host-pointer entry points.
 struct DevBuf {
     void *p = nullptr;

@@ -488,7 +488,8 @@ int hx_ffa(const uint32_t *counts, int64_t n_raw, int64_t bin_period, int nharm,
         hx::set_error("hx_ffa: bad arguments");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     hx::DevBuf dc, ds;
     HX_CUDA_TRY(dc.alloc((size_t)n_raw * sizeof(uint32_t)));
     HX_CUDA_TRY(ds.alloc((size_t)ntables * sizeof(double)));

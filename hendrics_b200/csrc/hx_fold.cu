@@ -1010,7 +1010,8 @@ int hx_fold_search(const double *times, int64_t n_ev, const double *freqs, int64
         hx::set_error("hx_fold_search: negative size");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     const size_t n_tr = (size_t)n_f * n_fd;
     if (n_tr == 0) return HX_OK;
     hx::DevBuf dt, df, dfd, ds, dp;

@@ -264,7 +264,8 @@ extern "C" int hx_microbench(int kind, int reps, double *ops_per_s, int device) 
         set_error("hx_microbench: bad arguments");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     DeviceInfo di;
     int rc = get_device_info(device, &di);
     if (rc) return rc;

@@ -219,7 +219,8 @@ int hx_orbital_search(const double *times, int64_t n_ev, double freq, double fdo
         hx::set_error("hx_orbital_search: bad arguments");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     if (n_t0 == 0) return HX_OK;
     hx::DevBuf dt, d0, ds, dp;
     HX_CUDA_TRY(dt.alloc((size_t)n_ev * 8));

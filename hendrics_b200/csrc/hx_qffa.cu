@@ -769,17 +769,19 @@ __global__ void __launch_bounds__(256) qffa_step2_kernel(const double *__restric
 // the group.  Sums of profiles are sums of their harmonic coefficients, so no profile is touched again.
 __global__ void __launch_bounds__(128) qffa_transient_kernel(const double *__restrict__ coef,
                                                              const unsigned long long *__restrict__ rowcnt,
-                                                             int nprof, int nharm, int n_levels,
-                                                             double *__restrict__ results /*[C][n_levels][nprof]*/) {
+                                                             int nprof, int nrows, int nharm, int n_levels,
+                                                             double *__restrict__ results /*[C][n_levels][nrows]*/) {
+    // nrows <= nprof: the reference keeps `profiles[:int(2 ** np.log2(nprof))]`, which drops the last time slice for
+    // about 40 % of the non power-of-two nprof (2 ** log2(10) = 9.999...); coef / rowcnt keep their nprof stride.
     const int c = blockIdx.z, level = blockIdx.y;
     const int n_ave = 1 << level;
-    const int groups = nprof / n_ave;  // int(profiles.shape[0] / n_ave_i)
+    const int groups = nrows / n_ave;  // int(profiles.shape[0] / n_ave_i)
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    double *out = results + ((size_t)c * n_levels + level) * nprof;
+    double *out = results + ((size_t)c * n_levels + level) * nrows;
     if (g >= groups) {
         // rows not covered by any group keep the reference's initial 0
         if (g == groups)
-            for (int r = groups * n_ave; r < nprof; r++) out[r] = 0.0;
+            for (int r = groups * n_ave; r < nrows; r++) out[r] = 0.0;
         return;
     }
     unsigned long long cnt = 0;
@@ -854,7 +856,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
                           const double *mean_f, const double *mean_fd, const double *mean_fdd, int64_t n_centres,
                           int nbin, int nprof, double delta0, double delta1, const double *d_L, const double *d_Q,
                           int64_t n_lq, const double *d_base, const double *d_tab, int nharm, double *d_stats,
-                          uint32_t *d_profiles, cudaStream_t st, int transient_levels) {
+                          uint32_t *d_profiles, cudaStream_t st, int transient_levels, int transient_rows) {
     const bool p2 = (nbin & (nbin - 1)) == 0;
     if (!g_qffa_lane || !g_qffa_fast || !p2 || nbin < 8 || nbin > 512 || n_centres < 1) return 1;
     int mode = 0;
@@ -1027,8 +1029,9 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         HX_CHECK_LAUNCH("qffa_rowdft_lane_kernel");
         if (transient_levels > 0) {
             dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
-            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, nharm,
-                                                       transient_levels, d_stats + (size_t)c0 * transient_levels * nprof);
+            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, transient_rows,
+                                                       nharm, transient_levels,
+                                                       d_stats + (size_t)c0 * transient_levels * transient_rows);
             HX_CHECK_LAUNCH("qffa_transient_kernel");
         } else if (nharm <= 4) {
             const int ppc = (int)std::min<int64_t>(64, n_lq);  // pairs per CTA; 256/ppc groups of time slices
@@ -1068,11 +1071,11 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
 }
 
 // transient_levels > 0: instead of the (L, Q) shift search, write the sub-interval statistics of the
-// transient search, d_stats[n_centres][transient_levels][nprof]
+// transient search, d_stats[n_centres][transient_levels][transient_rows]
 int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double t_last, const double *mean_f,
                          const double *mean_fd, const double *mean_fdd, int64_t n_centres, int nbin, int nprof,
                          const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
-                         uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0) {
+                         uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0, int transient_rows = 0) {
     std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_t || !mean_f || !mean_fd || !mean_fdd || !L || !Q || !d_stats) {
         set_error("hx_qffa_search: null pointer argument");
@@ -1142,7 +1145,7 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
         // preferred path: lane = centre (conflict-free atomics); falls through when not eligible
         int rl = qffa_lane_path(di, d_t, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin, nprof,
                                 delta0, delta1, d_L, d_Q, n_lq, d_base, d_tab, nharm, d_stats, d_profiles, st,
-                                transient_levels);
+                                transient_levels, transient_rows);
         if (rl <= 0) return rl;
     }
     const size_t prof_elems = (size_t)nprof * nbin;
@@ -1249,9 +1252,9 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
         HX_CHECK_LAUNCH("qffa_rowdft_kernel");
         if (transient_levels > 0) {
             dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
-            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, nharm,
-                                                       transient_levels,
-                                                       d_stats + (size_t)c0 * transient_levels * nprof);
+            qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, transient_rows,
+                                                       nharm, transient_levels,
+                                                       d_stats + (size_t)c0 * transient_levels * transient_rows);
             HX_CHECK_LAUNCH("qffa_transient_kernel");
         } else {
             dim3 g2((unsigned)n_lq, (unsigned)C);
@@ -1278,7 +1281,7 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
         const int saved = g_qffa_fast;
         g_qffa_fast = 0;
         int rc = qffa_search_dev_impl(d_t, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin, nprof, L,
-                                      Q, n_lq, nharm, d_stats, d_profiles, st, transient_levels);
+                                      Q, n_lq, nharm, d_stats, d_profiles, st, transient_levels, transient_rows);
         g_qffa_fast = saved;
         return rc;
     }
@@ -1321,8 +1324,8 @@ int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, do
 
 int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last,
                             const double *mean_f, const double *mean_fd, int64_t n_centres, int nbin, int nprof,
-                            int nharm, int n_levels, double *d_stats, void *stream) {
-    if (n_levels < 1 || n_levels > 30 || n_centres < 0 || !mean_f || !mean_fd) {
+                            int nprof_used, int nharm, int n_levels, double *d_stats, void *stream) {
+    if (n_levels < 1 || n_levels > 30 || n_centres < 0 || !mean_f || !mean_fd || nprof_used < 1 || nprof_used > nprof) {
         hx::set_error("hx_transient_search_dev: bad arguments");
         return HX_ERR_ARG;
     }
@@ -1330,7 +1333,7 @@ int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_firs
     const double one_lq[1] = {0.0};
     return hx::qffa_search_dev_impl(d_times_c, n_ev, t_first, t_last, mean_f, mean_fd, zeros.data(), n_centres, nbin,
                                     nprof, one_lq, one_lq, 1, nharm, d_stats, nullptr,
-                                    reinterpret_cast<cudaStream_t>(stream), n_levels);
+                                    reinterpret_cast<cudaStream_t>(stream), n_levels, nprof_used);
 }
 
 int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, const double *mean_fd,
@@ -1340,7 +1343,8 @@ int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, co
         hx::set_error("hx_qffa_search: bad arguments");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     hx::DevBuf dt, ds, dp;
     HX_CUDA_TRY(dt.alloc((size_t)n_ev * 8));
     HX_CUDA_TRY(ds.alloc((size_t)n_centres * n_lq * 8));

@@ -132,7 +132,8 @@ int hx_topk(const double *stats, int64_t n, int k, int64_t *idx, double *val, in
         hx::set_error("hx_topk: null pointer");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     hx::DevBuf d;
     HX_CUDA_TRY(d.alloc((size_t)std::max<int64_t>(n, 0) * 8));
     if (n > 0) HX_CUDA_TRY(cudaMemcpy(d.p, stats, (size_t)n * 8, cudaMemcpyHostToDevice));

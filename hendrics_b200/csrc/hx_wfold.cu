@@ -722,7 +722,8 @@ int hx_wfold_search(const double *times, const double *weights, double unit_weig
         hx::set_error("hx_wfold_search: bad sizes");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     const size_t n_tr = (size_t)n_f * n_fd;
     if (n_tr == 0) return HX_OK;
     hx::DevBuf dt, dw, df, dfd, ds, dp;

@@ -201,7 +201,8 @@ int hx_zn_unbinned(const double *times, int64_t n_ev, const double *freqs, int64
         hx::set_error("hx_zn_unbinned: bad arguments");
         return HX_ERR_ARG;
     }
-    HX_CUDA_TRY(cudaSetDevice(device));
+    hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
+    HX_CUDA_TRY(dev_guard.enter(device));
     const size_t n_tr = (size_t)n_f * n_fd;
     if (n_tr == 0) return HX_OK;
     bool has_fd = false;

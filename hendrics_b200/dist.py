@@ -43,31 +43,80 @@ def shard_bounds(n, world, r):
     return lo, lo + base + (1 if r < extra else 0)
 
 
+def _to_host(x):
+    """Device tensor -> numpy through ONE copy into page-locked memory (torch's caching host allocator; the array
+    keeps the block alive)."""
+    import torch
+
+    if x.device.type != "cuda":
+        return x.contiguous().numpy()
+    host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    host.copy_(x)
+    return host.numpy()
+
+
 def all_gather_concat(local, counts, axis=-1):
-    """All-gather ragged fp64 slices (``counts[r]`` entries along ``axis`` on rank r) and
-    concatenate them in rank order.  Uses the backend's device (cuda for NCCL, cpu for gloo)."""
+    """All-gather ragged fp64 slices (``counts[r]`` entries along ``axis`` on rank r) and concatenate them in rank
+    order.  ``local`` is a numpy array or a torch tensor already on the backend's device (cuda for NCCL, cpu for
+    gloo).  The statistics never visit the host on the way: one ``all_gather_into_tensor`` into a contiguous
+    (world, ..., max count) buffer, the rank-order concatenation on the device, one device-to-host copy."""
     import torch
 
     d = _dist()
-    local = np.moveaxis(np.asarray(local, dtype=np.float64), axis, -1)
-    lead = local.shape[:-1]
-    cmax = int(max(counts))
+    ws = d.get_world_size()
     use_cuda = d.get_backend() == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
-    buf = torch.zeros(lead + (cmax,), dtype=torch.float64, device=dev)
-    if local.shape[-1] > 0:
-        buf[..., : local.shape[-1]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
-    parts = [torch.empty_like(buf) for _ in range(d.get_world_size())]
-    d.all_gather(parts, buf)
-    out = np.concatenate([p[..., : int(c)].cpu().numpy() for p, c in zip(parts, counts)], axis=-1)
-    return np.moveaxis(out, -1, axis)
+    if not isinstance(local, torch.Tensor):
+        local = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    local = local.to(device=dev, dtype=torch.float64).movedim(axis, -1)
+    lead = tuple(local.shape[:-1])
+    cmax = int(max(counts))
+    if local.shape[-1] == cmax:
+        buf = local.contiguous()
+    else:
+        buf = torch.zeros(lead + (cmax,), dtype=torch.float64, device=dev)
+        buf[..., : local.shape[-1]] = local
+    parts = torch.empty((ws,) + lead + (cmax,), dtype=torch.float64, device=dev)
+    d.all_gather_into_tensor(parts.view(-1), buf.view(-1))  # flat views: accepted by NCCL and gloo alike
+    if all(int(c) == cmax for c in counts) and not lead:
+        out = parts.reshape(-1)
+    else:
+        out = torch.cat([parts[r][..., : int(c)] for r, c in enumerate(counts)], dim=-1)
+    return np.moveaxis(_to_host(out), -1, axis)
+
+
+def _raise_together(err):
+    """One rank failing (e.g. HxRangeError for its slice) must not leave the others blocked in the all-gather:
+    agree on an error flag first and raise on every rank."""
+    import torch
+
+    d = _dist()
+    use_cuda = d.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=dev)
+    d.all_reduce(flag, op=d.ReduceOp.MAX)
+    if err is not None:
+        raise err
+    if int(flag.item()):
+        raise RuntimeError("sharded search: another rank failed on its slice of the trial grid")
+
+
+def _call_local(fn):
+    try:
+        res, err = fn(), None
+    except Exception as e:  # noqa: BLE001 - re-raised by _raise_together on every rank
+        res, err = None, e
+    _raise_together(err)
+    return res
 
 
 def sharded_search(func, times, trial_freqs, fdots=0, **kwargs):
     """``func(times, trial_freqs, fdots=..., **kwargs)`` with the frequency axis sharded over ranks.
 
     ``func`` follows the z_n_search / epoch_folding_search convention: returns ``(fgrid, stats)`` for a
-    single fdot, else ``(fgrid, fdgrid, stats)`` with stats of shape ``(n_fdot, n_freq)``."""
+    single fdot, else ``(fgrid, fdgrid, stats)`` with stats of shape ``(n_fdot, n_freq)``.  This package's own
+    searches (marked ``_hx_device_stats``) hand their slice over as a device tensor, so the statistics go
+    kernel -> NCCL -> one D2H copy."""
     trial_freqs = np.atleast_1d(np.asarray(trial_freqs, dtype=np.float64))
     ws = world_size()
     if ws == 1 or trial_freqs.size < ws:
@@ -75,11 +124,16 @@ def sharded_search(func, times, trial_freqs, fdots=0, **kwargs):
     r = rank()
     bounds = [shard_bounds(trial_freqs.size, ws, i) for i in range(ws)]
     lo, hi = bounds[r]
-    res = func(times, trial_freqs[lo:hi], fdots=fdots, **kwargs)
-    stats = all_gather_concat(res[-1], [b[1] - b[0] for b in bounds], axis=-1)
+    if getattr(func, "_hx_device_stats", False) and _dist().get_backend() == "nccl":
+        kwargs = dict(kwargs, _device_stats=True)
+    res = _call_local(lambda: func(times, trial_freqs[lo:hi], fdots=fdots, **kwargs))
     fd = np.atleast_1d(np.asarray(fdots, dtype=np.float64))
+    local = res[-1]
+    if len(res) == 2 and fd.size == 1:
+        local = local.reshape(1, -1)
+    stats = all_gather_concat(local, [b[1] - b[0] for b in bounds], axis=-1)
     if len(res) == 2:
-        return trial_freqs.copy(), stats
+        return trial_freqs.copy(), stats.reshape(-1)
     fgrid, fdgrid = np.meshgrid(trial_freqs, fd)
     return fgrid, fdgrid, stats
 
@@ -93,5 +147,5 @@ def sharded_rows(local_fn, rows):
         return np.asarray(local_fn(rows))
     bounds = [shard_bounds(rows.shape[0], ws, i) for i in range(ws)]
     lo, hi = bounds[rank()]
-    local = np.asarray(local_fn(rows[lo:hi]))
+    local = _call_local(lambda: local_fn(rows[lo:hi]))
     return all_gather_concat(local, [b[1] - b[0] for b in bounds], axis=0)

@@ -517,8 +517,11 @@ def transient_search(
         allvalues = [0]
     cents = np.array([[np.double(frequency + step * i + 0.12 * step), np.double(fdot + 0)] for i in allvalues])
     dt = (times[-1] - times[0]) / nprof
-    # `nprof = int(2 ** np.log2(nprof))` in the reference does not truncate
-    n_levels = int(np.log2(int(2 ** np.log2(nprof))))
+    # `nprof = int(2 ** np.log2(nprof))` (hendrics/efsearch.py:436-438) is not a power-of-two truncation, but the
+    # floating-point round trip does drop the LAST time slice for some nprof (10 -> 9, 100 -> 99, 200 -> 199): the
+    # events are histogrammed into nprof slices and the averaging sees the first nprof_used of them
+    nprof_used = int(2 ** np.log2(nprof))
+    n_levels = int(np.log2(nprof_used))
     nave = 2 ** np.arange(n_levels)
 
     times_d = _to_device(times)
@@ -528,11 +531,11 @@ def transient_search(
 
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         mf, mfd = np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1])
-        out = torch.empty((rows.shape[0], n_levels, nprof), dtype=torch.float64, device=times_d.device)
+        out = torch.empty((rows.shape[0], n_levels, nprof_used), dtype=torch.float64, device=times_d.device)
         with torch.cuda.device(times_d.device):
             rc = _cabi.lib().hx_transient_search_dev(
                 times_d.data_ptr(), times_d.numel(), float(times[0]), float(times[-1]), _cabi.dptr(mf),
-                _cabi.dptr(mfd), rows.shape[0], int(nbin), int(nprof), int(n), int(n_levels), out.data_ptr(),
+                _cabi.dptr(mfd), rows.shape[0], int(nbin), int(nprof), int(nprof_used), int(n), int(n_levels), out.data_ptr(),
                 torch.cuda.current_stream().cuda_stream,
             )
         _cabi.check(rc)
@@ -696,12 +699,12 @@ def _common_parser(args=None):
                         "derivative using an optimized step. This option ignores expocorr, fdotmin/max, "
                         "segment-size, and step")
     parser.add_argument("--ffa", default=False, action="store_true",
-                        help="Use *the* Fast Folding Algorithm by Staelin+69. (not available in hendrics_b200)")
+                        help="Use *the* Fast Folding Algorithm by Staelin+69. No accelerated search allowed at the moment. Only recommended to search for slow pulsars.")
     parser.add_argument("--transient", default=False, action="store_true",
                         help="Look for transient emission (the dynamic Z search arrays are saved as "
                         "<root>_transient.npz; the reference's animated GIF needs matplotlib)")
     parser.add_argument("--expocorr", default=False, action="store_true",
-                        help="Correct for the exposure of the profile bins (not available in hendrics_b200)")
+                        help="Correct for the exposure of the profile bins. This method is *much* slower, but it is useful for very slow pulsars, where data gaps due to occultation or SAA passages can significantly alter the exposure of different profile bins.")
     parser.add_argument("--find-candidates", default=False, action="store_true",
                         help="Find pulsation candidates using thresholding")
     parser.add_argument("--conflevel", default=99, type=float, help="percent confidence level for thresholding [0-100).")

@@ -82,6 +82,7 @@ def _folding_search(
     flags=0,
     return_profiles=False,
     exact_phase=False,
+    _device_stats=False,
 ):
     """Upstream ``_folding_search`` fast branch with the (fdot, f) double loop
     replaced by one K1 launch per segment.
@@ -140,19 +141,25 @@ def _folding_search(
         else:
             stats_d += res
         count += 1
-    out = _grids_and_stats(frequencies, fdots, stats_d, count)
+    out = _grids_and_stats(frequencies, fdots, stats_d, count, device_stats=_device_stats)
     if return_profiles:
         out = out + (prof_d.cpu().numpy(),)
     return out
 
 
-def _grids_and_stats(frequencies, fdots, stats_d, count):
+def _grids_and_stats(frequencies, fdots, stats_d, count, device_stats=False):
     """Return tuple of upstream's ``_folding_search``: ``(fgrid.flatten(), stats.flatten() / count)`` for a single
     fdot, else ``(fgrid, fdgrid, stats / count)`` with shape (n_fdot, n_freq).  The division (same IEEE operation as
-    numpy's) runs on the device and the 1-D case skips the meshgrid: no extra host passes over 10^6-trial arrays."""
+    numpy's) runs on the device and the 1-D case skips the meshgrid: no extra host passes over 10^6-trial arrays.
+    ``device_stats`` (multi-GPU path, ``dist.sharded_search``): the statistics stay a device tensor -- they go
+    straight into the NCCL all-gather -- and no grids are built for the slice."""
+    from .dist import _to_host
+
     torch = _torch()
     stats_d = stats_d / count if count > 0 else torch.full_like(stats_d, float("nan"))  # upstream: 0 / 0
-    stats = stats_d.cpu().numpy()
+    if device_stats:
+        return (frequencies, stats_d) if fdots.size == 1 else (frequencies, fdots, stats_d)
+    stats = _to_host(stats_d)
     if fdots.size == 1:
         return frequencies, stats.reshape(-1)  # `frequencies` is already this call's own astype() copy
     fgrid, fdgrid = np.meshgrid(frequencies, fdots)
@@ -194,7 +201,7 @@ def wfold_stats_device(ts_d, w_d, unit_weight, freqs_d, fdots_d, nbin, nharm, gt
 
 def _folding_search_weighted(
     nharm, times, frequencies, nbin=128, segment_size=np.inf, fdots=0, expocorr=False, gti=None, weights=1,
-    device=None, return_profiles=False,
+    device=None, return_profiles=False, _device_stats=False,
 ):
     """Upstream ``_folding_search(..., use_times=True)`` with the per-trial
     ``fold_events`` + statistic replaced by one K1w launch per segment.  As upstream: times are re-zeroed to
@@ -264,7 +271,7 @@ def _folding_search_weighted(
         else:
             stats_d += res
         count += 1
-    out = _grids_and_stats(frequencies, fdots, stats_d, count)
+    out = _grids_and_stats(frequencies, fdots, stats_d, count, device_stats=_device_stats)
     if return_profiles:
         out = out + (prof_d.cpu().numpy(),)
     return out
@@ -307,6 +314,11 @@ def z_n_search(
         return _folding_search_weighted(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots,
                                         expocorr=expocorr, gti=gti, weights=weights, **kwargs)
     return _folding_search(nharm, times, frequencies, nbin=nbin, segment_size=segment_size, fdots=fdots, **kwargs)
+
+
+# dist.sharded_search may ask these for their statistics as a device tensor (`_device_stats=True`)
+epoch_folding_search._hx_device_stats = True
+z_n_search._hx_device_stats = True
 
 
 def fold_profiles(times, frequencies, fdots=0, nbin=128, nharm=0, device=None, flags=0, exact_phase=False):

@@ -134,11 +134,14 @@ int hx_qffa_search_dev(const double *d_times_c, int64_t n_ev, double t_first, do
  * Replaces hendrics/efsearch.py:468-485 (_transient_search_step) = _fast_phase_fdot + histogram2d +
  * _average_and_z_sub_search (:407-465) for `n_centres` centre frequencies: for every averaging level
  * l < n_levels (groups of 2^l consecutive time slices) the Z^2_nharm of each group's summed profile.
- *   d_stats [n_centres * n_levels * nprof]   (centre, level, time slice)
- * n_levels = int(log2(nprof)) in the reference.  Same conventions as hx_qffa_search_dev. */
+ *   d_stats [n_centres * n_levels * nprof_used]   (centre, level, time slice)
+ * The events are histogrammed into nprof time slices; the averaging uses the first nprof_used of them:
+ * nprof_used = int(2 ** np.log2(nprof)) and n_levels = int(np.log2(nprof_used)) in the reference (:436-441) -- the
+ * floating-point round trip drops the last slice for some non power-of-two nprof (10 -> 9, 100 -> 99), which the
+ * caller reproduces with numpy.  Same conventions as hx_qffa_search_dev. */
 int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_first, double t_last,
                             const double *mean_f, const double *mean_fd, int64_t n_centres, int nbin, int nprof,
-                            int nharm, int n_levels, double *d_stats, void *stream);
+                            int nprof_used, int nharm, int n_levels, double *d_stats, void *stream);
 
 /* ---- orbital-demodulation fold (widening) -------------------------------
  * Replaces the T0 loop of hendrics/efsearch.py:294-302 (folding_orbital_search): for every trial epoch of ascending

@@ -788,7 +788,8 @@ def search_with_qffa(
 # transient search (hendrics/efsearch.py:407-650)
 # --------------------------------------------------------------------------------------
 def average_and_z_sub_search(profiles, n=2):
-    """hendrics/efsearch.py:407-465 (`int(2 ** np.log2(nprof))` does not truncate, as in the reference)."""
+    """hendrics/efsearch.py:407-465.  `int(2 ** np.log2(nprof))` is no power-of-two truncation, but it does drop the
+    last slice for some nprof (10 -> 9, 100 -> 99: floating-point round trip), exactly as in the reference."""
     profiles = np.asarray(profiles, dtype=np.float64)
     nprof = len(profiles)
     nprof = int(2 ** np.log2(nprof))

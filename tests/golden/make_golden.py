@@ -172,6 +172,11 @@ def main():
     tr = hef.transient_search(ts, 9.88, 9.92, fdot=1e-6, nbin=32, nprof=96, n=1, oversample=2)
     out["transient_np96"] = dict(times=ts, nave=np.asarray(tr.nave), freqs=np.asarray(tr.freqs), tgrid=np.asarray(tr.times),
                                  stats=np.asarray(tr.stats))
+    # nprof = 100: `int(2 ** np.log2(100))` is 99 (floating-point round trip), so the reference histograms 100 time
+    # slices and averages the first 99 -- results have 99 columns and int(99 / 2^l) groups per level
+    tr = hef.transient_search(ts[:6000], 9.88, 9.92, nbin=16, nprof=100, n=2, oversample=2)
+    out["transient_np100"] = dict(times=ts[:6000], nave=np.asarray(tr.nave), freqs=np.asarray(tr.freqs),
+                                  tgrid=np.asarray(tr.times), stats=np.asarray(tr.stats))
 
     # ---- 8. fast folding algorithm, --ffa (in-tree: ffa.py:210-395, efsearch.py:1092-1138) -------
     hffa.show_progress = lambda x: x

@@ -134,7 +134,9 @@ def test_transient_search_oracle_vs_reference():
     np.testing.assert_allclose(res, g["results"], rtol=1e-12)
     assert np.all(res[0, 5] == 0)  # empty sub-profile keeps the initial 0
     for name, kw in (("transient_full", dict(nbin=16, n=2, oversample=4, f0=9.85, f1=9.95)),
-                     ("transient_np96", dict(nbin=32, nprof=96, n=1, oversample=2, f0=9.88, f1=9.92, fdot=1e-6))):
+                     ("transient_np96", dict(nbin=32, nprof=96, n=1, oversample=2, f0=9.88, f1=9.92, fdot=1e-6)),
+                     # nprof = 100 -> int(2 ** np.log2(100)) = 99 slices are averaged (the last one is dropped)
+                     ("transient_np100", dict(nbin=16, nprof=100, n=2, oversample=2, f0=9.88, f1=9.92))):
         g = load(name)
         kw = dict(kw)
         f0, f1 = kw.pop("f0"), kw.pop("f1")

@@ -167,6 +167,22 @@ assert np.array_equal(got3[0], full3[0]) and np.array_equal(got3[1], full3[1])
 rows = np.arange(11 * 3, dtype=np.float64).reshape(11, 3)
 out = hd.sharded_rows(lambda r: r[:, :1] * np.ones((1, 4)), rows)
 assert out.shape == (11, 4) and np.array_equal(out[:, 0], rows[:, 0])
+# a failure on one rank is raised on every rank instead of dead-locking the all-gather
+def bad(times, f, fdots=0, **kw):
+    if dist.get_rank() == 1:
+        raise ValueError("boom")
+    return O.z_n_search(times, f, fdots=fdots, **kw)
+try:
+    hd.sharded_search(bad, ts, freqs, fdots=0, nharm=2, nbin=32)
+    raise SystemExit("no error raised")
+except (ValueError, RuntimeError) as e:
+    assert ("boom" in str(e)) == (dist.get_rank() == 1), str(e)
+# torch tensors (the device-resident path of the CUDA searches) gather like numpy arrays
+import torch
+r = dist.get_rank()
+loc = torch.arange(3 * (4 + r), dtype=torch.float64).reshape(3, 4 + r) + 100 * r
+out = hd.all_gather_concat(loc, [4, 5], axis=-1)
+assert out.shape == (3, 9) and out[0, 0] == 0 and out[0, 4] == 100 and out[2, 8] == 100 + 14
 print("rank", dist.get_rank(), "ok")
 dist.destroy_process_group()
 """
