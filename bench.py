@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the HENDRICS periodicity-search hot path on B200 ("Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c4|c5|w1|w2|ffa] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c1|c2|c4|c5|zn|w1|w2|ffa] [--scaling strong|weak]
+                    [--impl reference]
 
-One "step" = one pass of the search over this rank's slice of the trial grid on a synthetic
-HENfake-style event list.  Default workload = BASELINE.json configs[1] (C2: HENefsearch, epoch
-folding nbin=16, 1e6 events x 1e6 trial frequencies per GPU; the frequency grid is sharded over
-ranks -- weak scaling -- and the statistic slices are all-gathered once per step).
+One "step" = one pass of the search over the trial grid on a synthetic HENfake-style event list.
+Default workload = the configuration BASELINE.json quotes its metric and target on (configs[2], "C3"):
+Z^2_4, nbin = 128, 1e7 events x 64 fdots x a 16384-frequency slab of the 1e6-frequency grid (one GPU's
+full share would take 26 s per step).  Default scaling is STRONG: the slab is FIXED and its frequency axis
+is sharded over the N ranks (events replicated, one all-gather of the statistic slices per step), so
+value(N) / value(1) is the fixed-problem speed-up the north star asks for.  `--scaling weak` gives every
+GPU 2048 frequencies instead; `--workload c2` is BASELINE.json configs[1] (epoch folding, nbin = 16).
 
 Prints ONE JSON line (rank 0).  `value` = event*trials/s with inputs resident in HBM (CUDA events);
 `e2e` = the same metric through the public API `hendrics_b200.epoch_folding_search` / `z_n_search`
@@ -34,14 +38,17 @@ if ROOT not in sys.path:
 METRIC = "Z_n^2 / epoch-folding search throughput (event*trials/s)"
 UNIT = "event*trials/s"
 
+# fixed frequency-grid width of the strong-scaling mode (split over the ranks); weak mode: n_freq per GPU below
+STRONG_N_FREQ = {"c1": 10_000, "c2": 1_000_000, "c3": 16_384, "c5": 32_768}
+
 # name -> (description, n_events, T, n_freq per GPU, f_start, f_step, n_fdot, fdot0, fdot_step, nbin, nharm, seed)
 WORKLOADS = {
     "c1": ("C1: HENzsearch Z^2_2, 1e5 events x 1e4 trial frequencies, nbin=128, no fdot",
            100_000, 1e5, 10_000, 9.876, 5e-6, 1, 0.0, 0.0, 128, 2, 1),
     "c2": ("C2: HENefsearch epoch folding nbin=16, 1e6 events x 1e6 trial frequencies",
            1_000_000, 1e5, 1_000_000, 7.4, 5e-6, 1, 0.0, 0.0, 16, 0, 2),
-    "c3": ("C3 slice: Z^2_4 nbin=128, 1e7 events x 2048 frequencies x 64 fdots per GPU "
-           "(full config: 1e6 frequencies sharded over 8 GPUs)",
+    "c3": ("C3 slab: Z^2_4 nbin=128, 1e7 events x 64 fdots x a slab of the 1e6-frequency grid "
+           "(full config: all 1e6 frequencies sharded over 8 GPUs)",
            10_000_000, 1e5, 2048, 7.4, 5e-6, 64, -1.6e-9, 5e-11, 128, 4, 3),
     "c5": ("C5 slice: Z^2_2 nbin=128, long baseline 1e8 s, 2e7 events x 4096 frequencies per GPU",
            20_000_000, 1e8, 4096, 9.9009, 5e-9, 1, 0.0, 0.0, 128, 2, 5),
@@ -59,15 +66,32 @@ def algorithmic_ops_per_evtr(n_fd_nonzero):
     return 6.0 if n_fd_nonzero else 4.0
 
 
-def make_inputs(wl, rank, world):
+def default_scaling(wl):
+    return "strong" if wl == "c3" else "weak"
+
+
+def make_inputs(wl, rank, world, scaling="weak"):
+    """Returns (desc, times, all_freqs, (lo, hi), fdots, nbin, nharm): the whole job's frequency grid and this
+    rank's contiguous slice of it.  weak: n_f frequencies per GPU; strong: STRONG_N_FREQ[wl] in total."""
+    from hendrics_b200.dist import shard_bounds
     from hendrics_b200.fake import simulate_events
 
     desc, n_ev, T, n_f, f0, fstep, n_fd, fd0, fdstep, nbin, nharm, seed = WORKLOADS[wl]
     times = simulate_events(n_ev, T, seed=seed)  # identical on every rank (replicated event list)
-    lo = rank * n_f  # contiguous frequency slice of the (world * n_f)-wide grid
-    freqs = f0 + fstep * (lo + np.arange(n_f, dtype=np.float64))
+    n_total = STRONG_N_FREQ[wl] if scaling == "strong" else n_f * world
+    all_freqs = f0 + fstep * np.arange(n_total, dtype=np.float64)
     fdots = fd0 + fdstep * np.arange(n_fd, dtype=np.float64) if n_fd > 1 else np.zeros(1)
-    return desc, times, freqs, fdots, nbin, nharm
+    return desc, times, all_freqs, shard_bounds(n_total, world, rank), fdots, nbin, nharm
+
+
+def fold_config(desc, nbin, nharm, n_events, n_freq_total, n_fdot, n_gpus, scaling):
+    """The `config` object of the JSON line -- built by BOTH arms from the same arguments, so the two lines
+    describe the same job key for key."""
+    return {"workload": desc, "nbin": int(nbin), "nharm": int(nharm), "n_events": int(n_events),
+            "n_freq_total": int(n_freq_total), "n_fdot": int(n_fdot), "scaling": scaling,
+            "parallelism": f"frequency axis of the trial grid sharded x{n_gpus}, events replicated, "
+                           "one all-gather of the statistic slices per step",
+            "l2": "flushed between timed iterations (256 MiB write)"}
 
 
 class ClockSampler:
@@ -140,7 +164,8 @@ def run_reference(args, wl):
         return
     if wl == "c4":
         return run_reference_c4(args)
-    desc, times, freqs, fdots, nbin, nharm = make_inputs(wl, 0, 1)
+    scaling = args.scaling or default_scaling(wl)
+    desc, times, freqs, _, fdots, nbin, nharm = make_inputs(wl, 0, max(args.gpus, 1), scaling)
     from oracle import c_oracle as C
 
     cores = C.max_threads()
@@ -164,9 +189,8 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(ts.size),
-                   "n_freq_per_gpu": int(freqs.size), "n_fdot": int(fdots.size)},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": fold_config(desc, nbin, nharm, ts.size, freqs.size, fdots.size, max(args.gpus, 1), scaling),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -724,26 +748,42 @@ def run_weighted(args):
         dist.destroy_process_group()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    wl = args.workload
-    if wl == "ffa":
-        return run_ffa_reference(args) if args.impl == "reference" else run_ffa(args)
-    if wl in WEIGHTED:
-        return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
-    if args.impl == "reference":
-        return run_reference(args, wl)
-    if wl == "c4":
-        return run_c4(args)
+def ncu_record(wl):
+    """Counters of the committed `ncu --set full` capture of this workload's bench command (profiles/), labelled with
+    their source file: DRAM bytes per launch (roofline.traffic) and the pipe utilisations.  They are NOT measured
+    in this run (a number taken under a profiler is never a bench value, and ncu cannot run inside the bench)."""
+    for rnd in ("r02", "r01"):
+        f = os.path.join(ROOT, "profiles", f"{rnd}_ncu_bench_{wl}_top.json")
+        if not os.path.exists(f):
+            continue
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
 
+        def num(key):
+            v = str(d.get(key, "")).split()
+            if not v:
+                return None
+            try:
+                x = float(v[0])
+            except ValueError:
+                return None
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(v[1], 1.0) if len(v) > 1 else 1.0
+            return x * mult
+
+        rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+        return {"source": f"ncu --set full, profiles/{os.path.basename(f)} (same bench command, earlier run)",
+                "kernel": d.get("Kernel Name"),
+                "dram_bytes_per_launch": (rd + wr) if rd is not None and wr is not None else None,
+                "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                "smem_pipe_pct": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active")}
+    return None
+
+
+def run_fold(args, wl):
+    """Exact-fold workloads (K1): c1, c2, c3 (default), c5."""
     import torch
     import torch.distributed as dist
 
@@ -758,9 +798,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from hendrics_b200 import _cabi, epoch_folding_search, z_n_search
+    from hendrics_b200 import dist as hdist
     from hendrics_b200.search import fold_stats_device
 
-    desc, times, freqs, fdots, nbin, nharm = make_inputs(wl, rank, world)
+    scaling = args.scaling or default_scaling(wl)
+    desc, times, all_freqs, (lo, hi), fdots, nbin, nharm = make_inputs(wl, rank, world, scaling)
+    freqs = np.ascontiguousarray(all_freqs[lo:hi])
+    counts = [b - a for a, b in (hdist.shard_bounds(all_freqs.size, world, r) for r in range(world))]
     has_fd = bool(np.any(fdots != 0))
     dev = torch.device("cuda", local_rank)
     # event selection of the public API (A1/A2), done once: resident inputs for the `value` leg
@@ -769,8 +813,8 @@ def main():
     ts_d = torch.from_numpy(ts_host).to(dev)
     f_d = torch.from_numpy(freqs).to(dev)
     fd_d = torch.from_numpy(fdots).to(dev)
-    n_tr_local = freqs.size * fdots.size
-    units_local = float(ts_host.size) * n_tr_local
+    units_local = float(ts_host.size) * freqs.size * fdots.size
+    units_total = float(ts_host.size) * all_freqs.size * fdots.size
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -778,12 +822,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = [torch.empty((fdots.size, freqs.size), dtype=torch.float64, device=dev) for _ in range(world)]
+    cmax = max(counts)
+    gathered = torch.empty((world, fdots.size, cmax), dtype=torch.float64, device=dev)
 
     def step_resident():
         stats = fold_stats_device(ts_d, f_d, fd_d, nbin, nharm)
-        if world > 1:
-            dist.all_gather(gathered, stats)  # the one data-path collective: statistic slices
+        if world > 1:  # the one data-path collective: statistic slices (padded to the widest slice)
+            if stats.shape[1] != cmax:
+                stats = torch.nn.functional.pad(stats, (0, cmax - stats.shape[1]))
+            dist.all_gather_into_tensor(gathered.view(-1), stats.contiguous().view(-1))
         return stats
 
     # ---- value: inputs resident in HBM -----------------------------------------------------
@@ -809,26 +856,23 @@ def main():
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) * 1e-3
-    value = units_local * world * args.steps / total_s
+    value = units_total * args.steps / total_s
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     kms, grid, block, smem = _cabi.fold_last_kernel()
     kern_avg_ms = float(np.mean(kern_ms))
 
-    # ---- e2e: public API, host arrays in, host arrays out --------------------------------------
+    # ---- e2e: the public API, host arrays in, host arrays out (every rank ends up with the full grid) -------
+    # z_n_search / epoch_folding_search on one GPU; the same functions through dist.sharded_search -- what
+    # hendrics_b200.efsearch.folding_search calls -- on N: H2D of the events + trial grid, kernels, NCCL all-gather of
+    # the device-resident statistic slices, one D2H copy.
     pin_t = torch.from_numpy(times).pin_memory()
-    pin_f = torch.from_numpy(freqs).pin_memory()
+    pin_f = torch.from_numpy(all_freqs).pin_memory()
     t_np, f_np = pin_t.numpy(), pin_f.numpy()
+    func = epoch_folding_search if nharm == 0 else z_n_search
+    kw = dict(nbin=nbin) if nharm == 0 else dict(nbin=nbin, nharm=nharm)
 
     def step_e2e():
-        if nharm == 0:
-            res = epoch_folding_search(t_np, f_np, nbin=nbin, fdots=fdots)
-        else:
-            res = z_n_search(t_np, f_np, nharm=nharm, nbin=nbin, fdots=fdots)
-        stats = res[-1]
-        if world > 1:
-            from hendrics_b200 import dist as hdist
-            stats = hdist.all_gather_concat(stats, [freqs.size] * world, axis=-1)
-        return stats
+        return hdist.sharded_search(func, t_np, f_np, fdots=fdots, **kw)[-1]
 
     for _ in range(2):
         step_e2e()
@@ -836,48 +880,48 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tq = time.perf_counter()
-        step_e2e()
+        stats_host = step_e2e()
         if os.environ.get("HX_BENCH_DEBUG"):
-            print(f"[debug] e2e step wall {time.perf_counter() - tq:.4f} s, kernel {_cabi.fold_last_kernel()}", file=sys.stderr)
+            print(f"[debug] rank {rank} e2e step wall {time.perf_counter() - tq:.4f} s, kernel {_cabi.fold_last_kernel()}", file=sys.stderr)
     barrier()
+    assert stats_host.size == all_freqs.size * fdots.size
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = units_local * world * args.steps / float(e2e_s.item())
-    h2d = times.nbytes + freqs.nbytes + fdots.nbytes
-    d2h = n_tr_local * 8
+    e2e_value = units_total * args.steps / float(e2e_s.item())
+    h2d = times.nbytes + freqs.nbytes + fdots.nbytes  # per rank
+    d2h = all_freqs.size * fdots.size * 8              # per rank: the whole statistic grid
 
     if rank == 0:
         # ---- roofline of the dominant kernel (K1 fold_kernel) ----------------------------------
         peak_ops = _cabi.microbench(1, reps=5, device=local_rank)  # DMUL+DADD issue rate, inst/s
         # attainable rate of the inner loop's instruction mix (no event loads, full occupancy), units/s
         mix_ceiling = _cabi.microbench(4 if has_fd else 5, reps=3, device=local_rank)
-        alg_ops = algorithmic_ops_per_evtr(has_fd) * units_local
-        achieved = alg_ops / (kern_avg_ms * 1e-3)
+        alg_per_unit = algorithmic_ops_per_evtr(has_fd)
+        alg_rate = alg_per_unit * units_local / (kern_avg_ms * 1e-3)
         shape = _cabi.fold_last_kernel_shape()  # instantiation of the timed launches
-        exec_ops = shape["fp64_per_unit"] * units_local / (kern_avg_ms * 1e-3)
+        exec_rate = shape["fp64_per_unit"] * units_local / (kern_avg_ms * 1e-3)
         # shared-memory data pipe: 1 wavefront/clk/SM; K1 needs one per increment (ATOMS) plus the broadcast event loads
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
         smem_peak_wf = n_sm * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         smem_wf = shape["smem_wavefronts_per_unit"] * units_local / 32.0 / (kern_avg_ms * 1e-3)
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", f"fold_{wl}_ncu_summary.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        ncu = ncu_record(wl)
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_gbs = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         roofline = {
-            "bound": "fp64_pipe", "achieved": achieved * 1e-12, "peak": peak_ops * 1e-12, "unit": "TFLOP/s",
-            "frac": achieved / peak_ops, "traffic": traffic,
-            "kernel": "hx::fold_kernel", "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
-            "algorithmic_fp64_ops_per_event_trial": algorithmic_ops_per_evtr(has_fd),
+            # what the hardware did: FP64 instructions issued by the inner loop / measured FP64 issue rate (<= 1)
+            "bound": "fp64_pipe", "achieved": exec_rate * 1e-12, "peak": peak_ops * 1e-12, "unit": "TFLOP/s",
+            "frac": exec_rate / peak_ops,
             "executed_fp64_ops_per_event_trial": shape["fp64_per_unit"],
-            "executed_fp64_frac": exec_ops / peak_ops,
             "smem_pipe_frac_model": smem_wf / smem_peak_wf,
             "smem_wavefronts_per_event_trial_model": shape["smem_wavefronts_per_unit"],
+            "ncu": ncu, "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+            "traffic_source": (ncu or {}).get("source"),
+            # SURVEY 8d's algorithmic count (6 FP64 ops per event*trial with fdot, 4 without); the kernel issues fewer
+            # instructions than that (pre-scaled constants, magic-add floor, shared fdot term), hence > executed
+            "algorithmic": {"fp64_ops_per_event_trial": alg_per_unit, "achieved": alg_rate * 1e-12,
+                            "frac": alg_rate / peak_ops},
+            "kernel": "hx::fold_kernel", "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
             "kernel_variant": {k: shape[k] for k in ("R", "mode", "rowfd", "m2t")},
             "mix_ceiling_units_per_s": mix_ceiling,
             "frac_of_mix_ceiling": units_local / (kern_avg_ms * 1e-3) / mix_ceiling,
@@ -888,18 +932,17 @@ def main():
         }
         cpu = None
         if not args.no_cpu_baseline:
-            v, cores, sample = cpu_port_throughput(times, freqs, fdots, nbin, nharm)
+            v, cores, sample = cpu_port_throughput(times, all_freqs, fdots, nbin, nharm)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc + " per GPU", "nbin": nbin, "nharm": nharm, "n_events": int(ts_host.size),
-                       "n_freq_per_gpu": int(freqs.size), "n_fdot": int(fdots.size),
-                       "parallelism": f"trial-grid sharding x{world}, events replicated, one all-gather of stats",
-                       "l2": "flushed between timed iterations (256 MiB write)"},
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": fold_config(desc, nbin, nharm, ts_host.size, all_freqs.size, fdots.size, world, scaling),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "hendrics_b200.dist.sharded_search(z_n_search | epoch_folding_search, ...) (= the call inside "
+                           "efsearch.folding_search); bytes are per rank"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -908,6 +951,31 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED))
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="exact-fold workloads: strong = fixed trial grid split over the ranks (default for c3), "
+                         "weak = fixed grid per GPU (default otherwise)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = args.workload
+    if wl == "ffa":
+        return run_ffa_reference(args) if args.impl == "reference" else run_ffa(args)
+    if wl in WEIGHTED:
+        return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    if wl == "c4":
+        return run_c4(args)
+    return run_fold(args, wl)
 
 
 if __name__ == "__main__":

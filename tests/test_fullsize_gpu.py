@@ -115,3 +115,96 @@ def test_flat_profile_identities_at_scale():
         s, p = fold_profiles(t, [f], [0.0], nbin=nbin, nharm=nharm)
         assert np.all(p == n // nbin)
         assert abs(s[0, 0]) < 1e-12 * n
+
+
+def test_c1_exact_baseline_shape_everything_against_oracle():
+    """C1 at its exact BASELINE shape (Z^2_2, 1e5 events x 1e4 trial frequencies, nbin = 128, no fdot): the oracle folds
+    all 1e9 event*trials in about a second, so EVERYTHING is compared -- all 1e4 statistics within 1e-9, all 1e4
+    profiles bit for bit, and the top-10 candidate list (value descending, ties by index) identical."""
+    from hendrics_b200 import z_n_search
+    from hendrics_b200.search import fold_profiles
+
+    ts = O.simulate_events(100_000, 1e5, seed=1) + 8e7  # NuSTAR-like absolute times, removed by the search (A1)
+    freqs = np.arange(9.876, 9.926 + 1e-8 * 5e-6, 5e-6)  # folding_search's grid for -f 9.876 -F 9.926, oversample 2
+    assert abs(freqs.size - 10_000) <= 1
+    f, stats = z_n_search(ts, freqs, nharm=2, nbin=128)
+    t = _selected(ts)
+    ref_s, ref_p = C.fold_search(t, freqs, [0.0], 128, 2, want_profiles=True)
+    assert np.array_equal(f, freqs)
+    np.testing.assert_allclose(stats, ref_s[0], rtol=RTOL)
+    s2, prof = fold_profiles(t, freqs, [0.0], nbin=128, nharm=2)
+    assert np.array_equal(prof, ref_p)  # 1e4 x 128 counts, bit-exact
+    np.testing.assert_allclose(s2[0], stats, rtol=1e-13)  # fused epilogue == scratch + fold_stat_kernel
+    assert np.array_equal(O.topk_flat(stats, 10)[0], O.topk_flat(ref_s[0], 10)[0])
+    # the public candidate finder (EFPeriodogram.find_peaks -> search_best_peaks) on both statistic arrays
+    from hendrics_b200.io import search_best_peaks
+
+    srt = np.sort(ref_s[0])
+    thr = 0.5 * (srt[-50] + srt[-51])  # between two values: a 1e-13 difference cannot move a run boundary
+    bx, bs = search_best_peaks(freqs, stats, thr)
+    rx, rs = search_best_peaks(freqs, ref_s[0], thr)
+    assert np.array_equal(bx, rx)
+    np.testing.assert_allclose(bs, rs, rtol=RTOL)
+    assert abs(freqs[np.argmax(stats)] - 1 / 0.101) < 1e-5
+
+
+def test_c3_bench_shape_profiles_bit_exact_through_packed_drains():
+    """C3 at the exact shape bench.py times per GPU at N = 8 (Z^2_4, nbin = 128, 1e7 events x 2048 f x 64 fdots): the
+    kernel variant is {R: 2, packed counters, shared fdot rows, fdot-term tile} and every CTA drains its packed
+    counters ~94 times.  Profiles of an 8 x 8 sub-grid (64 trials spread over the grid) are compared bit for bit with
+    the oracle at the full event count, their statistics within 1e-9, plus the conserved-count property on all
+    131 072 profiles."""
+    from hendrics_b200 import _cabi
+    from hendrics_b200.search import fold_profiles
+
+    ts = O.simulate_events(10_000_000, 1e5, seed=3)
+    t = _selected(ts)
+    freqs = 7.4 + 5e-6 * np.arange(2048)
+    fdots = -1.6e-9 + 5e-11 * np.arange(64)
+    stats, prof = fold_profiles(t, freqs, fdots, nbin=128, nharm=4)
+    shape = _cabi.fold_last_kernel_shape()
+    assert (shape["R"], shape["mode"], shape["rowfd"], shape["m2t"]) == (2, 2, 1, 1), shape
+    assert prof.shape == (64, 2048, 128)
+    assert np.all(prof.sum(axis=-1) == t.size)  # every event in exactly one bin of every one of the 131 072 trials
+    jf = np.array([0, 31, 32, 63, 64, 1000, 2016, 2047])  # lane / warp / CTA boundaries of the trial layout
+    ifd = np.array([0, 1, 17, 31, 32, 33, 62, 63])
+    ref_s, ref_p = C.fold_search(t, freqs[jf], fdots[ifd], 128, 4, want_profiles=True)
+    got_p = prof[np.ix_(ifd, jf)]
+    assert np.array_equal(got_p, ref_p)
+    np.testing.assert_allclose(stats[np.ix_(ifd, jf)], ref_s, rtol=RTOL)
+
+
+def _poisson_times(n, T, seed, f0=1 / 0.101, amp=0.25):
+    """n sorted event times on [0, T) from a rate ~ 1 + amp cos(2 pi f0 t), sorted BY CONSTRUCTION (cumulative sum of
+    exponential gaps, then thinning): no 1e8-element sort."""
+    rng = np.random.default_rng(seed)
+    m = int(n * (1 + amp) * 1.02) + 1000
+    t = np.cumsum(rng.exponential(T / m, m))
+    keep = rng.uniform(0, 1 + amp, m) < 1 + amp * np.cos(2 * np.pi * f0 * t)
+    t = t[keep][:n]
+    assert t.size == n
+    return t
+
+
+def test_c5_full_event_count_long_baseline():
+    """C5 at its BASELINE size: 1e8 events over ~1e8 s (1e9 pulse cycles), Z^2_2, nbin = 128, trial frequencies at the
+    step 1/(2T) around the pulse.  The whole 4096-frequency block runs on the GPU; a subset of its trials is folded by
+    the oracle at the full event count: statistics within 1e-9, profiles bit for bit (the fp64 phase has only ~23
+    fractional bits left at 1e9 cycles -- any deviation from the reference's rounding sequence would move counts)."""
+    from hendrics_b200 import z_n_search
+    from hendrics_b200.search import fold_profiles
+
+    T = 1e8
+    ts = _poisson_times(100_000_000, T, seed=5)
+    freqs = 1 / 0.101 + 5e-9 * (np.arange(4096) - 2048)
+    f, stats = z_n_search(ts, freqs, nharm=2, nbin=128)
+    assert stats.shape == (4096,) and np.all(np.isfinite(stats))
+    t = _selected(ts)
+    pick = np.array([0, 1, 63, 64, 2047, 2048, 2049, 4095])
+    ref_s, ref_p = C.fold_search(t, freqs[pick], [0.0], 128, 2, want_profiles=True)
+    np.testing.assert_allclose(stats[pick], ref_s[0], rtol=RTOL)
+    s2, prof = fold_profiles(t, freqs[pick], [0.0], nbin=128, nharm=2)
+    assert np.array_equal(prof, ref_p)
+    np.testing.assert_allclose(s2[0], ref_s[0], rtol=RTOL)
+    # the injected pulsation is recovered at the resolution of the grid
+    assert abs(f[np.argmax(stats)] - 1 / 0.101) <= 2 * 5e-9
