@@ -33,6 +33,8 @@ SIGNATURES = {
     "hx_launch_count": (_i64, []),
     "hx_fold_search": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _int, _uint, _c_dp, _c_u32p, _int]),
     "hx_fold_search_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _uint, _vp, _vp, _vp]),
+    "hx_fold_windows_dev": (_int, [_vp, _i64, _c_dp, _c_dp, _i64, _int, _dbl, _dbl, _vp, _i64, _vp, _i64, _int, _int, _vp, _vp,
+                                   ctypes.POINTER(_int), _vp]),
     "hx_wfold_search": (_int, [_c_dp, _c_dp, _dbl, _i64, _c_dp, _i64, _c_dp, _i64, _int, _int, _c_dp, _i64, _dbl, _dbl,
                                _c_dp, _c_dp, _int]),
     "hx_wfold_search_dev": (_int, [_vp, _vp, _dbl, _i64, _vp, _i64, _vp, _i64, _int, _int, _c_dp, _i64, _dbl, _dbl,

@@ -226,7 +226,13 @@ def time_intervals_from_gtis(gtis, segment_size, fraction_step=1):
 
 def dyn_folding_search(events, fmin, fmax, step=None, func=epoch_folding_search, oversample=2, time_step=128, **kwargs):
     """hendrics/efsearch.py:1196-1243 without the matplotlib figure: the same search repeated in
-    ``time_step``-long windows.  Returns ``(times, frequencies, stats[n_windows, n_freq])``."""
+    ``time_step``-long windows.  Returns ``(times, frequencies, stats[n_windows, n_freq])``.
+
+    With this package's own searches and windows too small to fill a GPU (the CLI's default: 128 s) all windows are
+    folded by ONE launch (``search.windowed_searches`` -> ``hx_fold_windows_dev``) and come back in one copy; otherwise
+    ``func`` is called window by window like in the reference."""
+    from . import search as _search
+
     if step is None:
         step = 1 / oversample / time_step
     gti = np.copy(events.gti)
@@ -234,23 +240,36 @@ def dyn_folding_search(events, fmin, fmax, step=None, func=epoch_folding_search,
     if not np.any(length > time_step):
         gti = np.array([[gti[0, 0], gti[-1, 1]]])
     start, stop = time_intervals_from_gtis(gti, time_step)
-    stats = []
     frequencies = np.arange(fmin, fmax, step)
     ev_time = np.asanyarray(events.time)
+    times = (start + stop) / 2
+
+    if func in (z_n_search, epoch_folding_search) and len(start) > 0 and len(start) <= 65535 and frequencies.size > 0:
+        kw = dict(kwargs)
+        nharm = kw.pop("nharm", 4) if func is z_n_search else 0
+        nbin = kw.pop("nbin", 128)
+        plain = (not kw.pop("expocorr", False) and kw.pop("gti", None) is None and np.isscalar(kw.pop("weights", 1))
+                 and np.all(np.asarray(kw.pop("fdots", 0)) == 0) and np.isinf(kw.pop("segment_size", np.inf)) and not kw)
+        small = ev_time.size / len(start) * frequencies.size <= _search.WINDOWED_MAX_UNITS_PER_WINDOW
+        if plain and small and len(start) * frequencies.size * 8 <= (1 << 30):
+            res = _search.windowed_searches(nharm, ev_time, frequencies, start, stop, nbin=nbin)
+            if res is not None:
+                return times, frequencies, res[0][:, 0, :]
+
+    stats = []
     is_sorted = ev_time.size < 2 or bool(np.all(ev_time[1:] >= ev_time[:-1]))
     for st, sp in zip(start, stop):
         if is_sorted:  # same selection as the mask below, without a pass over the whole list per window
             times_filt = ev_time[np.searchsorted(ev_time, st, side="left"):np.searchsorted(ev_time, sp, side="left")]
         else:
             times_filt = ev_time[(ev_time >= st) & (ev_time < sp)]
-        trial_freqs = np.arange(fmin, fmax, step)
         try:
-            frequencies, stat = func(times_filt, trial_freqs, **kwargs)
+            frequencies, stat = func(times_filt, frequencies, **kwargs)
             stats.append(stat)
         except _cabi.HxError:
             raise
         except Exception:
-            stats.append(np.zeros_like(trial_freqs))
+            stats.append(np.zeros_like(frequencies))
     times = (start + stop) / 2
     return times, frequencies, np.array(stats)
 

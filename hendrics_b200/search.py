@@ -19,7 +19,7 @@ import numpy as np
 from . import _cabi
 
 __all__ = ["z_n_search", "epoch_folding_search", "fold_profiles", "fold_profiles_weighted", "orbital_fold_stats",
-           "z_n_search_unbinned",
+           "z_n_search_unbinned", "windowed_searches", "fold_windows_device",
            "UPSTREAM_SEMANTICS"]
 
 # The two places where the restatement of stingray's `_folding_search` could not be checked against
@@ -69,6 +69,65 @@ def fold_stats_device(ts_d, freqs_d, fdots_d, nbin, nharm, flags=0, want_profile
         )
     _cabi.check(rc)
     return (stats, prof) if want_profiles else stats
+
+
+# A window (segment / dynamical-search step) this small cannot fill the GPU by itself: all windows go through ONE
+# hx_fold_windows_dev launch.  Above it, one K1 launch per window is the faster plan (K1 is ~10x quicker per unit).
+WINDOWED_MAX_UNITS_PER_WINDOW = 1.0e8
+
+WIN_SEGMENTS, WIN_SEARCHES = 0, 1
+
+
+def fold_windows_device(ts_d, win_start, win_stop, mode, freqs_d, fdots_d, nbin, nharm, origin=0.0, segment_size=0.0,
+                        want_sum=False):
+    """One ``hx_fold_windows_dev`` call on a sorted device event list.  Returns ``(stats (n_win, n_fd, n_f) tensor,
+    status int32[n_win] (1 folded, 0 skipped, 2 upstream raises), sum (n_fd, n_f) tensor or None)``."""
+    import ctypes
+
+    torch = _torch()
+    win_start = np.ascontiguousarray(win_start, dtype=np.float64)
+    win_stop = np.ascontiguousarray(win_stop, dtype=np.float64)
+    n_win, n_f, n_fd = win_start.size, freqs_d.numel(), fdots_d.numel()
+    stats = torch.empty((n_win, n_fd, n_f), dtype=torch.float64, device=ts_d.device)
+    total = torch.empty((n_fd, n_f), dtype=torch.float64, device=ts_d.device) if want_sum else None
+    status = np.zeros(n_win, dtype=np.int32)
+    ts_d = ts_d.contiguous()
+    with torch.cuda.device(ts_d.device):
+        rc = _cabi.lib().hx_fold_windows_dev(
+            ts_d.data_ptr(), ts_d.numel(), _cabi.dptr(win_start), _cabi.dptr(win_stop), n_win, int(mode), float(origin),
+            float(segment_size), freqs_d.data_ptr(), n_f, fdots_d.data_ptr(), n_fd, int(nbin), int(nharm),
+            stats.data_ptr(), total.data_ptr() if want_sum else None, status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+            torch.cuda.current_stream().cuda_stream,
+        )
+    _cabi.check(rc)
+    return stats, status, total
+
+
+def _is_sorted_device(t_d):
+    return t_d.numel() < 2 or bool((t_d[1:] >= t_d[:-1]).all().item())
+
+
+def windowed_searches(nharm, times, frequencies, starts, stops, nbin=128, fdots=0, device=None):
+    """``[func(times[(times >= st) & (times < sp)], frequencies, ...) for st, sp in zip(starts, stops)]`` -- the loop of
+    ``dyn_folding_search`` (hendrics/efsearch.py:1221-1231) -- in one launch, for sorted ``times``.  Returns
+    ``(stats (n_windows, n_fdot, n_freq) numpy, status int32[n_windows])``; rows with status 0 are NaN (upstream's 0/0),
+    rows with status 2 are zeros (upstream raises; the caller stores zeros).  None when ``times`` is not sorted."""
+    from .dist import _to_host
+
+    torch = _torch()
+    dev = _device(device)
+    times = np.asanyarray(times)
+    if times.dtype != np.float64:
+        return None  # extended-precision times are re-zeroed on the host per window: keep the per-window calls
+    frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
+    fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
+    ts_d = torch.from_numpy(np.ascontiguousarray(times)).to(dev)
+    if not _is_sorted_device(ts_d):
+        return None
+    f_d = torch.from_numpy(np.ascontiguousarray(frequencies)).to(dev)
+    fd_d = torch.from_numpy(np.ascontiguousarray(fdots)).to(dev)
+    stats, status, _ = fold_windows_device(ts_d, starts, stops, WIN_SEARCHES, f_d, fd_d, nbin, nharm)
+    return _to_host(stats), status
 
 
 def _folding_search(
@@ -122,6 +181,14 @@ def _folding_search(
     stats_d = torch.zeros(grid_shape, dtype=torch.float64, device=dev)
     prof_d = torch.zeros(grid_shape + (nbin,), dtype=torch.int64, device=dev) if return_profiles else None
     count = 0
+    n_seg = len(start_times)
+    if (n_seg > 1 and n_seg <= 65535 and not return_profiles and flags == 0 and UPSTREAM_SEMANTICS["drop_last_event"]
+            and times_d.numel() / n_seg * grid_shape[0] * grid_shape[1] <= WINDOWED_MAX_UNITS_PER_WINDOW
+            and n_seg * grid_shape[0] * grid_shape[1] * 8 <= (1 << 30) and _is_sorted_device(times_d)):
+        # many small segments (--segment-size): one launch for all of them, summed in segment order on the device
+        _, status, total = fold_windows_device(times_d, start_times, start_times + segment_size, WIN_SEGMENTS, freqs_d,
+                                               fdots_d, nbin, nharm, origin=0.0, segment_size=segment_size, want_sum=True)
+        return _grids_and_stats(frequencies, fdots, total, int(np.count_nonzero(status == 1)), device_stats=_device_stats)
     for s in start_times:
         if UPSTREAM_SEMANTICS["drop_last_event"]:
             good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open

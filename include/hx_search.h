@@ -80,6 +80,28 @@ int hx_fold_search_dev(const double *d_times, int64_t n_ev, const double *d_freq
                        const double *d_fdots, int64_t n_fd, int nbin, int nharm, unsigned flags, double *d_stats,
                        uint32_t *d_profiles, void *stream);
 
+/* ---- K1win: the exact fold search on many small time windows, one launch --------------------------
+ * Replaces (a) the window loop of dyn_folding_search (hendrics/efsearch.py:1221-1231; run by default by the CLI for
+ * observations longer than --dynstep, :1912-1922) and (b) the segment loop of stingray's _folding_search as driven by
+ * `--segment-size` (hendrics/efsearch.py:1658-1663): per window the same per-trial fold + statistic as hx_fold_search.
+ *   d_times [n_ev]              event times, SORTED ascending, device
+ *   win_start, win_stop [n_win] HOST arrays: window w holds the events with win_start[w] <= x < win_stop[w], where
+ *     mode 0 (segments of ONE search): x = fl(t - origin), the times re-zeroed once; a window with no event or whose
+ *             events span < 0.2 * segment_size is skipped, as upstream skips it (status 0);
+ *     mode 1 (independent searches):   x = t (raw times); the window is then searched like upstream searches a whole
+ *             event list: re-zeroed to ITS first event, events at its last time dropped (half-open single segment),
+ *             skipped when the rest spans < 0.2 of its length (status 0: upstream returns 0/0 = NaN); an empty or
+ *             zero-length window makes upstream raise, for which dyn_folding_search stores zeros (status 2).
+ *   d_stats [n_win * n_fd * n_f] statistics per window (NaN for status 0, 0 for status 2)
+ *   d_sum   [n_fd * n_f] or NULL: sum over the folded windows in window order (upstream's `stats += stat`)
+ *   h_status[n_win]             HOST array of the status codes above (1 = folded).  Synchronizes `stream`.
+ * Meant for windows too small to fill the GPU one by one (reference operation sequence, events read from global
+ * memory); large windows are better served by one hx_fold_search_dev call each. */
+int hx_fold_windows_dev(const double *d_times, int64_t n_ev, const double *win_start, const double *win_stop,
+                        int64_t n_win, int mode, double origin, double segment_size, const double *d_freqs, int64_t n_f,
+                        const double *d_fdots, int64_t n_fd, int nbin, int nharm, double *d_stats, double *d_sum,
+                        int *h_status, void *stream);
+
 /* ---- K1w: weighted / exposure-corrected fold search ------------------------------------------
  * Replaces the SLOW branch of stingray.pulse.search._folding_search (use_times=True ->
  * stingray.pulse.pulsar.fold_events per trial), which z_n_search / epoch_folding_search take when

@@ -355,8 +355,8 @@ def folding_search_core(
         else:
             _search_serial(ts, frequencies, fdots, nbin, nharm, ctab, stab, stats, profiles, return_profiles)
         count += 1
-    if count > 0:
-        stats = stats / count
+    with np.errstate(invalid="ignore", divide="ignore"):
+        stats = stats / count  # Appendix A: unguarded; no folded segment gives 0/0 = NaN (and numpy's warning)
     if fgrid.shape[0] == 1:
         out = (fgrid.flatten(), stats.flatten())
     else:
@@ -502,8 +502,8 @@ def folding_search_slow(
                 if return_profiles:
                     profiles[i, j] += prof
         count += 1
-    if count > 0:
-        stats = stats / count
+    with np.errstate(invalid="ignore", divide="ignore"):
+        stats = stats / count  # Appendix A: unguarded; no folded segment gives 0/0 = NaN (and numpy's warning)
     if fgrid.shape[0] == 1:
         out = (fgrid.flatten(), stats.flatten())
     else:
