@@ -12,7 +12,6 @@ Event input: the reference reads mission FITS / HENDRICS event files through sti
 
 from __future__ import annotations
 
-import copy
 import glob
 import os
 import pickle
@@ -149,91 +148,100 @@ def search_best_peaks(x, stat, threshold):
     return [best_x[o] for o in order], [best_stat[o] for o in order]
 
 
+# (field, default) in the order hendrics/io.py:85-105 assigns them; the saved file is the dict of these attributes, so
+# the names are the file format
+_EF_FIELDS = (
+    ("freq", None), ("stat", None), ("kind", None), ("nbin", None), ("oversample", None), ("N", None), ("peaks", None),
+    ("peak_stat", None), ("best_fits", None), ("fdots", 0), ("fddots", 0), ("M", None), ("segment_size", 1e32),
+    ("filename", ""), ("parfile", None), ("emin", None), ("emax", None), ("pepoch", None), ("mjdref", None),
+    ("upperlim", None), ("ncounts", None),
+)
+_EF_POSITIONAL = ("freq", "stat", "kind", "nbin", "N", "oversample", "M", "pepoch", "mjdref", "peaks", "peak_stat",
+                  "best_fits", "fdots", "fddots", "segment_size", "filename", "parfile", "emin", "emax", "ncounts",
+                  "upperlim")
+_CLASS_TAG = "__sr__class__type__"
+
+
 class EFPeriodogram:
-    """Same fields as hendrics/io.py:60-105."""
+    """Result of a folding search: the container of hendrics/io.py:60-105 (same constructor signature, positional
+    order included, same attributes)."""
 
-    def __init__(self, freq=None, stat=None, kind=None, nbin=None, N=None, oversample=None, M=None, pepoch=None,
-                 mjdref=None, peaks=None, peak_stat=None, best_fits=None, fdots=0, fddots=0, segment_size=1e32,
-                 filename="", parfile=None, emin=None, emax=None, ncounts=None, upperlim=None):
-        self.freq = freq
-        self.stat = stat
-        self.kind = kind
-        self.nbin = nbin
-        self.oversample = oversample
-        self.N = N
-        self.peaks = peaks
-        self.peak_stat = peak_stat
-        self.best_fits = best_fits
-        self.fdots = fdots
-        self.fddots = fddots
-        self.M = M
-        self.segment_size = segment_size
-        self.filename = filename
-        self.parfile = parfile
-        self.emin = emin
-        self.emax = emax
-        self.pepoch = pepoch
-        self.mjdref = mjdref
-        self.upperlim = upperlim
-        self.ncounts = ncounts
+    def __init__(self, *args, **kwargs):
+        if len(args) > len(_EF_POSITIONAL):
+            raise TypeError(f"EFPeriodogram takes at most {len(_EF_POSITIONAL)} positional arguments")
+        given = dict(zip(_EF_POSITIONAL, args))
+        for k in kwargs:
+            if k not in _EF_POSITIONAL:
+                raise TypeError(f"EFPeriodogram got an unexpected keyword argument {k!r}")
+            if k in given:
+                raise TypeError(f"EFPeriodogram got multiple values for argument {k!r}")
+        given.update(kwargs)
+        for name, default in _EF_FIELDS:
+            setattr(self, name, given.get(name, default))
 
-    def find_peaks(self, conflevel=99.0):
-        """hendrics/io.py:107-144."""
+    def detection_threshold(self, conflevel=99.0):
+        """Statistic value exceeded by noise with probability 1 - conflevel/100 over the independent trials of the plane
+        (trials / oversample), for this periodogram's statistic."""
         ntrial = self.stat.size
-        if hasattr(self, "oversample") and self.oversample is not None:
-            ntrial /= self.oversample
-            ntrial = int(ntrial)
+        if getattr(self, "oversample", None) is not None:
+            ntrial = int(ntrial / self.oversample)
         epsilon = 1 - conflevel / 100
         if self.kind == "Z2n":
-            threshold = z2_n_detection_level(epsilon=epsilon, n=self.N, ntrial=ntrial, n_summed_spectra=int(self.M))
+            return z2_n_detection_level(epsilon=epsilon, n=self.N, ntrial=ntrial, n_summed_spectra=int(self.M))
+        return fold_detection_level(nbin=int(self.nbin), epsilon=epsilon, ntrial=ntrial)
+
+    def find_peaks(self, conflevel=99.0):
+        """Peaks above the ``conflevel`` threshold (hendrics/io.py:107-144): for a 1-D periodogram the maxima of the
+        regions above it, for a plane the ten highest pixels as (f, fdot) pairs.  Stores them in ``peaks`` /
+        ``peak_stat`` when there are any and returns ``(peaks, peak_stat)``."""
+        threshold = self.detection_threshold(conflevel)
+        stat = np.asarray(self.stat)
+        if stat.ndim == 1:
+            peaks, heights = search_best_peaks(self.freq, stat, threshold)
+            peaks, heights = np.asarray(peaks), np.asarray(heights)
         else:
-            threshold = fold_detection_level(nbin=int(self.nbin), epsilon=epsilon, ntrial=ntrial)
-        if len(self.stat.shape) == 1:
-            best_peaks, best_stat = search_best_peaks(self.freq, self.stat, threshold)
-        else:
-            best_cands = find_peaks_in_image(self.stat, n=10, threshold_abs=threshold)
-            best_peaks, best_stat = [], []
-            for idx in best_cands:
-                best_peaks.append([self.freq[idx[0], idx[1]], self.fdots[idx[0], idx[1]]])
-                best_stat.append(self.stat[idx[0], idx[1]])
-        best_peaks = np.asarray(best_peaks)
-        best_stat = np.asarray(best_stat)
-        if len(best_peaks) > 0:
-            self.peaks = best_peaks
-            self.peak_stat = best_stat
-        return best_peaks, best_stat
+            at = find_peaks_in_image(stat, n=10, threshold_abs=threshold)
+            rows, cols = (at[:, 0], at[:, 1]) if len(at) else (np.zeros(0, dtype=int),) * 2
+            peaks = np.stack([np.asarray(self.freq)[rows, cols], np.asarray(self.fdots)[rows, cols]], axis=1)
+            heights = stat[rows, cols]
+        if len(peaks) > 0:
+            self.peaks, self.peak_stat = peaks, heights
+        return peaks, heights
+
+
+def _model_file(fname, i):
+    return fname.replace(HEN_FILE_EXTENSION, f"__mod{i}__.p")
 
 
 def save_folding(efperiodogram, fname):
-    """hendrics/io.py:656-671 (pickle back-end; fitted models are pickled into side files)."""
-    outdata = copy.copy(efperiodogram.__dict__)
-    outdata["__sr__class__type__"] = "EFPeriodogram"
-    if "best_fits" in outdata and efperiodogram.best_fits is not None:
-        for i, b in enumerate(efperiodogram.best_fits):
-            mfile = fname.replace(HEN_FILE_EXTENSION, f"__mod{i}__.p")
-            with open(mfile, "wb") as fobj:
-                pickle.dump(b, fobj)
-        outdata.pop("best_fits")
+    """Pickle back-end of hendrics/io.py:656-671: ``fname`` holds the attribute dict plus the class tag; every entry of
+    ``best_fits`` goes to its own ``<root>__mod<i>__.p`` side file instead."""
+    content = dict(vars(efperiodogram))
+    content[_CLASS_TAG] = "EFPeriodogram"
+    fits = content.get("best_fits")
+    if fits is not None:
+        del content["best_fits"]
+        for i, model in enumerate(fits):
+            with open(_model_file(fname, i), "wb") as fobj:
+                pickle.dump(model, fobj)
     with open(fname, "wb") as fobj:
-        pickle.dump(outdata, fobj)
+        pickle.dump(content, fobj)
 
 
 def load_folding(fname):
-    """hendrics/io.py:674-696."""
+    """Inverse of :func:`save_folding` (hendrics/io.py:674-696): side files found next to ``fname`` become
+    ``best_fits``; a scalar ``peaks`` is wrapped in a list."""
     with open(fname, "rb") as fobj:
-        data = pickle.load(fobj)
-    data.pop("__sr__class__type__")
+        content = pickle.load(fobj)
+    content.pop(_CLASS_TAG)
     ef = EFPeriodogram()
-    for key in data.keys():
-        setattr(ef, key, data[key])
-    modelfiles = sorted(glob.glob(fname.replace(HEN_FILE_EXTENSION, "__mod*__.p")))
-    if len(modelfiles) >= 1:
-        bmodels = []
-        for mfile in modelfiles:
-            if os.path.exists(mfile):
-                with open(mfile, "rb") as fobj:
-                    bmodels.append(pickle.load(fobj))
-        ef.best_fits = bmodels
-    if ef.peaks is not None and len(np.asarray(ef.peaks).shape) == 0:
+    vars(ef).update(content)
+    side_files = sorted(glob.glob(_model_file(fname, "*")))
+    if side_files:
+        ef.best_fits = []
+        for mfile in side_files:
+            with open(mfile, "rb") as fobj:
+                ef.best_fits.append(pickle.load(fobj))
+    if ef.peaks is not None and np.ndim(ef.peaks) == 0:
         ef.peaks = [ef.peaks]
     return ef

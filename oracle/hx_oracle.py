@@ -572,21 +572,31 @@ def folding_search(
 # --------------------------------------------------------------------------------------
 # hendrics/efsearch.py:263-310 folding_orbital_search (T0 loop of one parameter row)
 # --------------------------------------------------------------------------------------
-def orbital_demodulate(times, T0, X, Porb):
-    """efsearch.py:295-296: two fixed-point iterations of the Roemer-delay removal."""
-    new_values = times - X * np.sin(2 * np.pi * (times - T0) / Porb)
-    new_values = new_values - X * np.sin(2 * np.pi * (new_values - T0) / Porb)
+def sin_correctly_rounded(a):
+    """fp64 sin rounded from an extended-precision evaluation (x87 long double: 64-bit mantissa, so the fp64 result is
+    the correctly rounded one except within ~2^-11 ulp of a rounding boundary).  ``np.sin`` on fp64 is NOT this
+    function: numpy dispatches to SIMD kernels with errors up to ~1 ulp that depend on the CPU's vector extensions
+    (0.12 % of random arguments differ in the last bit on the AVX-512 build measured in tests/test_oracle.py), so the
+    reference's demodulated times are only defined up to the libm / SIMD flavour it runs on."""
+    return np.sin(np.asarray(a, dtype=np.longdouble)).astype(np.float64)
+
+
+def orbital_demodulate(times, T0, X, Porb, sin=np.sin):
+    """efsearch.py:295-296: two fixed-point iterations of the Roemer-delay removal (``sin``: the reference's
+    ``np.sin``; ``sin_correctly_rounded`` to measure how much the choice of sin implementation moves)."""
+    new_values = times - X * sin(2 * np.pi * (times - T0) / Porb)
+    new_values = new_values - X * sin(2 * np.pi * (new_values - T0) / Porb)
     return new_values
 
 
-def orbital_stats(times, freq, fdot, X, Porb, T0s, fun=None, return_profiles=False, **fun_kwargs):
+def orbital_stats(times, freq, fdot, X, Porb, T0s, fun=None, return_profiles=False, sin=np.sin, **fun_kwargs):
     """efsearch.py:294-302: ``fun(new_values, np.array([freq]), fdots=fdot, **fun_kwargs)[1][0]`` for every T0."""
     if fun is None:
         fun = epoch_folding_search
     stats = np.zeros(len(T0s))
     profs = []
     for k, T0 in enumerate(T0s):
-        nv = orbital_demodulate(times, T0, X, Porb)
+        nv = orbital_demodulate(times, T0, X, Porb, sin=sin)
         res = fun(nv, np.array([freq]), fdots=fdot, return_profiles=return_profiles, **fun_kwargs)
         stats[k] = res[1][0]
         if return_profiles:

@@ -64,6 +64,16 @@ def test_zsearch_fast_cli(evfile):
     ef = load_folding(out[0])
     assert len(ef.fdots) > 1
     assert os.path.exists(out[0] + "_best_cands.csv")
+    # f1 outputs (hendrics/efsearch.py:1516-1533): the cuts through every detected candidate, read by HENplot
+    from hendrics_b200.candidates import CandTable
+
+    cands = CandTable.read(out[0] + "_best_cands.csv")
+    root = out[0][:-2]
+    side = sorted(f for f in os.listdir(os.path.dirname(out[0])) if os.path.basename(root) + "_cand_" in f)
+    n_det = int(np.sum(~np.isnan(np.asarray(cands["pulse_amp"], dtype=float))))
+    assert n_det >= 1 and len(side) == 2 * n_det
+    cut = CandTable.read(os.path.join(os.path.dirname(out[0]), [f for f in side if "_cand_4_fdot" in f][0]))
+    assert cut.colnames == ["freq", "stat"] and np.array_equal(cut["stat"], ef.stat[cands["f_idx"][0], :])
     i = np.unravel_index(np.argmax(ef.stat), ef.stat.shape)
     assert np.isclose(ef.freq[i], PULSE_F, atol=2 / 25.25)
 

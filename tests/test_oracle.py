@@ -136,3 +136,24 @@ def test_slow_branch_reduces_to_fast_branch():
     np.testing.assert_allclose(a[1], b[1], rtol=1e-13)
     with pytest.raises(ValueError, match="specify the GTIs"):
         O.epoch_folding_search(ts, f, expocorr=True)
+
+
+def test_orbital_profiles_do_not_depend_on_the_sin_flavour():
+    """Row f4: folding_orbital_search goes through two ``np.sin`` per event (hendrics/efsearch.py:295-296) and numpy's
+    fp64 sin is a SIMD kernel whose last bit depends on the CPU (it differs from the correctly rounded value for ~0.1 %
+    of arguments on AVX-512).  That does not reach the profiles: X*sin is far smaller than t, the rounded difference
+    rarely changes, and a last-bit change of a time almost never crosses a bin edge.  So bit-exact profile parity is a
+    meaningful bar for the orbital kernel too (tests/test_orbital_gpu.py), whatever sin the host library uses."""
+    f0, X, Porb, T0 = 1.2345, 3.0, 5000.0, 1234.0
+    te = O.simulate_events(40001, 20000.0, f0=f0, amp=0.8, seed=16)
+    ts = np.sort(te + X * np.sin(2 * np.pi * (te - T0) / Porb))
+    T0s = np.concatenate([[T0], np.random.default_rng(1).uniform(0, Porb, 30)])
+    s_np, p_np = O.orbital_stats(ts, f0, 0.0, X, Porb, T0s, fun=O.epoch_folding_search, return_profiles=True, nbin=16)
+    s_cr, p_cr = O.orbital_stats(ts, f0, 0.0, X, Porb, T0s, fun=O.epoch_folding_search, return_profiles=True, nbin=16,
+                                 sin=O.sin_correctly_rounded)
+    assert np.array_equal(p_np, p_cr) and np.array_equal(s_np, s_cr)
+    a = np.random.default_rng(0).uniform(-50, 50, 200000)
+    assert np.mean(np.sin(a) != O.sin_correctly_rounded(a)) < 0.01
+    # the demodulated times themselves: a last-bit difference for a small fraction of the events at most
+    d_np, d_cr = O.orbital_demodulate(ts, T0, X, Porb), O.orbital_demodulate(ts, T0, X, Porb, sin=O.sin_correctly_rounded)
+    assert np.mean(d_np != d_cr) < 0.01 and np.max(np.abs(d_np - d_cr)) <= np.spacing(ts.max())

@@ -1,7 +1,9 @@
 """Orbital-demodulation fold (hendrics/efsearch.py:263-310) against the oracle's restatement of the T0 loop.
-sin() is CUDA's on the device and numpy's in the oracle: the demodulated times may differ in the last bit, so a
-photon can move to the neighbouring bin.  Bar: profiles equal up to a handful of +-1 moves between adjacent bins,
-statistics within 1e-6 (bit-exact parity is not claimed for this row)."""
+sin() is CUDA's on the device (<= 2 ulp) and numpy's SIMD kernel in the oracle (<= 1 ulp, CPU dependent): the two may
+differ in the last bit of sin, but X*sin is ~1e4 times smaller than t, so the rounded difference t - X*sin changes in
+its last bit for ~1e-3 of the events only, and such a change crosses a bin edge with probability ~ulp(t)*f*nbin ~ 1e-10.
+Measured (profiles/r02_orbital_diff.txt): all 4 x 71 profiles of these cases are IDENTICAL to the oracle's, with
+numpy's sin and with a correctly rounded sin alike.  Bar: profile counts bit-exact, statistics within 1e-9, like K1."""
 import os
 
 import numpy as np
@@ -30,9 +32,8 @@ def test_orbital_stats_vs_oracle(nbin, nharm, fdot):
     kw = dict(nbin=nbin) if nharm == 0 else dict(nbin=nbin, nharm=nharm)
     ref_s, ref_p = O.orbital_stats(ts, f0, fdot, X, Porb, T0s, fun=fun, return_profiles=True, **kw)
     assert prof.shape == ref_p.shape and np.array_equal(prof.sum(axis=1), ref_p.sum(axis=1))
-    moved = np.abs(prof - ref_p).sum(axis=1)
-    assert moved.max() <= 4 and (moved > 0).mean() < 0.2, moved
-    np.testing.assert_allclose(stats, ref_s, rtol=1e-6)
+    assert np.array_equal(prof, ref_p), np.abs(prof - ref_p).sum(axis=1)
+    np.testing.assert_allclose(stats, ref_s, rtol=1e-9)
     # demodulating at the true epoch concentrates the pulsed power; a typical wrong epoch smears it
     assert stats[0] > 2 * np.median(stats)
 
@@ -49,8 +50,8 @@ def test_orbital_event_splits_and_c_abi():
                                        _cabi.dptr(stats), prof.ctypes.data_as(_cabi._c_u32p), 0)
     _cabi.check(rc)
     ref_s, ref_p = O.orbital_stats(ts, f0, 0.0, X, Porb, T0s, fun=O.epoch_folding_search, return_profiles=True, nbin=16)
-    assert np.abs(prof.astype(np.int64) - ref_p).sum() <= 8
-    np.testing.assert_allclose(stats, ref_s, rtol=1e-6)
+    assert np.array_equal(prof.astype(np.int64), ref_p)
+    np.testing.assert_allclose(stats, ref_s, rtol=1e-9)
     assert _cabi.lib().hx_orbital_search(_cabi.dptr(ts), ts.size, f0, 0.0, X, -1.0, _cabi.dptr(T0s), 5, 16, 0,
                                          _cabi.dptr(stats), None, 0) == _cabi.HX_ERR_ARG
 
