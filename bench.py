@@ -748,6 +748,191 @@ def run_weighted(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# K4: unbinned Z^2_n (the north star's own kernel sketch: one sin/cos per event*trial + angle-addition recurrence)
+# ---------------------------------------------------------------------------------------------
+# (description, n_events, T, n_freq per GPU, f0, f_step, n_fdot, fdot0, fdot_step, nharm, seed)
+ZN = {
+    "zn": ("ZN: unbinned Z^2_2 (z_n_fast over an (f, fdot) grid), 1e6 events x 8192 frequencies x 8 fdots per GPU",
+           1_000_000, 1e5, 8192, 9.88, 5e-6, 8, -2e-10, 5e-11, 2, 7),
+    "zn4": ("ZN4: unbinned Z^2_4, 1e6 events x 8192 frequencies x 8 fdots per GPU",
+            1_000_000, 1e5, 8192, 9.88, 5e-6, 8, -2e-10, 5e-11, 4, 7),
+    "zn1": ("ZN1: unbinned Z^2_2 on the C1 shape, 1e5 events x 1e4 frequencies, no fdot",
+            100_000, 1e5, 10_000, 9.876, 5e-6, 1, 0.0, 0.0, 2, 1),
+}
+
+
+def zn_inputs(wl, rank, world):
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, n_f, f0, fstep, n_fd, fd0, fdstep, nharm, seed = ZN[wl]
+    times = simulate_events(n_ev, T, seed=seed)
+    all_freqs = f0 + fstep * np.arange(n_f * world, dtype=np.float64)
+    fdots = fd0 + fdstep * np.arange(n_fd, dtype=np.float64) if n_fd > 1 else np.zeros(1)
+    return desc, times, all_freqs, (rank * n_f, (rank + 1) * n_f), fdots, nharm
+
+
+def zn_config(desc, nharm, n_events, n_freq_total, n_fdot, n_gpus):
+    return {"workload": desc, "nharm": int(nharm), "n_events": int(n_events), "n_freq_total": int(n_freq_total),
+            "n_fdot": int(n_fdot), "scaling": "weak",
+            "parallelism": f"frequency axis of the trial grid sharded x{n_gpus}, events replicated, "
+                           "one all-gather of the statistic slices per step",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def zn_cpu_rate(times, freqs, fdots, nharm, target_s=8.0):
+    """The oracle's unbinned Z^2_n (numpy, one thread: the reference's z_n_fast is a serial numba function) on the
+    first S trials of the workload."""
+    from oracle import hx_oracle as O
+
+    def one(f, fd):
+        ph = times * f + 0.5 * times * times * fd
+        ph -= np.floor(ph)
+        return O.z_n_events(ph, nharm)
+
+    t0 = time.perf_counter()
+    one(freqs[0], fdots[0])
+    per = max(time.perf_counter() - t0, 1e-5)
+    n = int(max(2, min(freqs.size, target_s / per)))
+    t0 = time.perf_counter()
+    for j in range(n):
+        one(freqs[j], fdots[0])
+    dt = time.perf_counter() - t0
+    return times.size * n / dt, 1, f"oracle z_n_events (numpy, 1 thread), {times.size} events x {n} trials, {dt:.1f} s"
+
+
+def run_zn_reference(args, wl):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    desc, times, freqs, _, fdots, nharm = zn_inputs(wl, 0, max(args.gpus, 1))
+    rate, cores, sample = zn_cpu_rate(times, freqs, fdots, nharm, target_s=3.0 * max(args.steps, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": zn_config(desc, nharm, times.size, freqs.size, fdots.size, max(args.gpus, 1)),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_zn(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hendrics_b200 import _cabi, z_n_search_unbinned
+
+    desc, times, all_freqs, (lo, hi), fdots, nharm = zn_inputs(wl, rank, world)
+    freqs = np.ascontiguousarray(all_freqs[lo:hi])
+    dev = torch.device("cuda", local_rank)
+    ts_d = torch.from_numpy(times).to(dev)
+    f_d = torch.from_numpy(freqs).to(dev)
+    fd_d = torch.from_numpy(fdots).to(dev)
+    stats_d = torch.empty((fdots.size, freqs.size), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world, fdots.size, freqs.size), dtype=torch.float64, device=dev)
+    units_local = float(times.size) * freqs.size * fdots.size
+    units_total = units_local * world
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    lib = _cabi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        _cabi.check(lib.hx_zn_unbinned_dev(ts_d.data_ptr(), ts_d.numel(), f_d.data_ptr(), f_d.numel(), fd_d.data_ptr(),
+                                           fd_d.numel(), nharm, stats_d.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), stats_d.view(-1))
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms, ops = [], 0
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+        ms, ops = _cabi.zn_last_kernel()
+        kern_ms.append(ms)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = units_total * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    kern_avg_ms = float(np.mean(kern_ms))
+
+    # e2e: the public API with host arrays (H2D of events + grid, kernels, D2H of the statistics), this rank's slice
+    pin_t = torch.from_numpy(times).pin_memory().numpy()
+    for _ in range(2):
+        z_n_search_unbinned(pin_t, freqs, nharm=nharm, fdots=fdots)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = z_n_search_unbinned(pin_t, freqs, nharm=nharm, fdots=fdots)[-1]
+    barrier()
+    assert out.size == freqs.size * fdots.size
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_total * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        peak_dfma = _cabi.microbench(0, reps=5, device=local_rank)  # FP64 instruction issue rate (DFMA), inst/s
+        exec_rate = ops * units_local / (kern_avg_ms * 1e-3)
+        ncu = ncu_record(wl)
+        roofline = {
+            "bound": "fp64_pipe", "achieved": exec_rate * 1e-12, "peak": peak_dfma * 1e-12, "unit": "TFLOP/s",
+            "frac": exec_rate / peak_dfma,
+            "note": "achieved = FP64 INSTRUCTIONS issued per second (an FMA counts 1, like a DMUL or a DADD: the pipe "
+                    "issues one per lane per slot whatever the opcode); peak = measured DFMA issue rate",
+            "executed_fp64_ops_per_event_trial": ops,
+            "ncu": ncu, "traffic": (ncu or {}).get("dram_bytes_per_launch"), "traffic_source": (ncu or {}).get("source"),
+            "kernel": "hx::zn_unbinned_kernel", "kernel_ms": kern_avg_ms,
+            "kernel_share_of_step": kern_avg_ms * args.steps / sum(step_ms),
+            "peak_source": "measured in this process: hx_microbench kind 0 (DFMA issue rate); MEASURED_PEAKS.json has no "
+                           "FP64 entry",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, sample = zn_cpu_rate(times, all_freqs, fdots, nharm)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": zn_config(desc, nharm, times.size, all_freqs.size, fdots.size, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(times.nbytes + freqs.nbytes + fdots.nbytes),
+                    "d2h_bytes_per_step": int(freqs.size * fdots.size * 8),
+                    "api": "hendrics_b200.z_n_search_unbinned(times, freqs, nharm, fdots) per rank on its slice"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def ncu_record(wl):
     """Counters of the committed `ncu --set full` capture of this workload's bench command (profiles/), labelled with
     their source file: DRAM bytes per launch (roofline.traffic) and the pipe utilisations.  They are NOT measured
@@ -959,7 +1144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED) + sorted(ZN))
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
                     help="exact-fold workloads: strong = fixed trial grid split over the ranks (default for c3), "
                          "weak = fixed grid per GPU (default otherwise)")
@@ -971,6 +1156,8 @@ def main():
         return run_ffa_reference(args) if args.impl == "reference" else run_ffa(args)
     if wl in WEIGHTED:
         return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
+    if wl in ZN:
+        return run_zn_reference(args, wl) if args.impl == "reference" else run_zn(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl)
     if wl == "c4":

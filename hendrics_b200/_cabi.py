@@ -49,6 +49,7 @@ SIGNATURES = {
     "hx_orbital_search_dev": (_int, [_vp, _i64, _dbl, _dbl, _dbl, _dbl, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "hx_zn_unbinned": (_int, [_c_dp, _i64, _c_dp, _i64, _c_dp, _i64, _int, _c_dp, _int]),
     "hx_zn_unbinned_dev": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "hx_zn_last_kernel_ms": (_int, [_c_dp, ctypes.POINTER(_int)]),
     "hx_topk": (_int, [_c_dp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _int]),
     "hx_topk_dev": (_int, [_vp, _i64, _int, _c_i64p, _c_dp, _c_i64p, _vp]),
     "hx_hist1d_dev": (_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp]),
@@ -166,6 +167,13 @@ def wfold_last_kernel():
     ms, k, n = _dbl(0.0), _int(-1), _i64(0)
     check(lib().hx_wfold_last_kernel_ms(ctypes.byref(ms), ctypes.byref(k), ctypes.byref(n)))
     return ms.value, k.value, n.value
+
+
+def zn_last_kernel():
+    """(ms, FP64 instructions per event*trial) of the last K4 (unbinned Z^2_n) launch."""
+    ms, ops = _dbl(0.0), _int(0)
+    check(lib().hx_zn_last_kernel_ms(ctypes.byref(ms), ctypes.byref(ops)))
+    return ms.value, ops.value
 
 
 def qffa_last_kernel():

@@ -286,14 +286,21 @@ struct QLaneArgs {
     uint32_t topbit;
     int pack_shift;
     int flush_events;  // packed: drain at least every this many events
-    uint32_t *prof;    // [ceil(n_c/32)][nprof][nbin][32]
+    uint32_t *prof;    // [ceil(n_c/32)][nprof][nbin][32]   (COEF = false)
     int warps;
     uint32_t hist_off, tile_off;
     int tile_ev;
     int *errflag;
+    // COEF = true: a finished time slice leaves the SM as its harmonic coefficients, not as its nbin counts
+    double *coef;                 // [n_c][nprof][nharm][2]  (Cr_h, Sr_h), accumulated with fp64 atomics
+    unsigned long long *rowcnt;   // [n_c][nprof] events of the slice
+    const double *tab;            // [2 * nbin] cos | sin (global); staged at extra_off
+    int nharm;                    // <= QL_NHMAX
+    uint32_t extra_off;           // tables [2 * nbin] then accumulators [warps * R][2 * nharm + 1][32] (doubles)
 };
+constexpr int QL_NHMAX = 4;
 
-template <int R, int MODE, bool PACKED>
+template <int R, int MODE, bool PACKED, bool COEF = false>
 __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int UE = 4;
@@ -311,6 +318,13 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
         return;
     }
     for (uint32_t o = tid * 4; o < (uint32_t)nwarps * R * blk; o += blockDim.x * 4) sts_u32(hist + o, 0u);
+    double *tsm = reinterpret_cast<double *>(smem + a.extra_off);   // COEF: cos | sin tables ...
+    double *accs = tsm + 2 * nbin;                                   // ... and this CTA's accumulators
+    const int nacc = 2 * a.nharm + 1;
+    if (COEF) {
+        for (int i = tid; i < 2 * nbin; i += blockDim.x) tsm[i] = a.tab[i];
+        for (int i = tid; i < nwarps * R * nacc * 32; i += blockDim.x) accs[i] = 0.0;
+    }
 
     // centre constants: slot = 32 centres
     const long long slot0 = ((long long)blockIdx.x * nwarps + warp) * R;
@@ -404,6 +418,81 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             }
         }
     };
+    // COEF: fold this thread's columns into its harmonic accumulators (partial DFT of the counts; a DFT is linear, so
+    // the packed counters can be emptied as often as they need) and clear them
+    auto accumulate = [&]() {
+        const double *tc = tsm, *ts = tsm + nbin;
+        const int nh = a.nharm;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double c[QL_NHMAX] = {0.0, 0.0, 0.0, 0.0}, sn[QL_NHMAX] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0;
+            if (PACKED) {
+                // bins w and w + nbin/2 share a word; harmonic k of bin w + nbin/2 is (-1)^k times that of bin w
+                const int half = nbin >> 1;
+                const uint32_t lowmask = topbit - 1u;
+                for (int w = 0; w < half; w++) {
+                    const uint32_t ad = cb[r] + ((uint32_t)w << 7);
+                    const uint32_t v = lds_u32(ad);
+                    if (v) {
+                        sts_u32(ad, 0u);
+                        const uint32_t up = v >> a.pack_shift, lowc = (v & lowmask) - up;
+                        const double dsum = (double)(lowc + up), ddif = (double)lowc - (double)up;
+                        cnt += dsum;
+#pragma unroll
+                        for (int h = 0; h < QL_NHMAX; h++)
+                            if (h < nh) {
+                                const int idx = ((h + 1) * w) & (nbin - 1);
+                                const double d = (h & 1) ? dsum : ddif;  // harmonic k = h + 1
+                                c[h] = __fma_rn(tc[idx], d, c[h]);
+                                sn[h] = __fma_rn(ts[idx], d, sn[h]);
+                            }
+                    }
+                }
+            } else {
+                for (int b = 0; b < nbin; b++) {
+                    const uint32_t ad = cb[r] + ((uint32_t)b << 7);
+                    const uint32_t v = lds_u32(ad);
+                    if (v) {
+                        sts_u32(ad, 0u);
+                        const double d = (double)v;
+                        cnt += d;
+#pragma unroll
+                        for (int h = 0; h < QL_NHMAX; h++)
+                            if (h < nh) {
+                                const int idx = ((h + 1) * b) & (nbin - 1);
+                                c[h] = __fma_rn(tc[idx], d, c[h]);
+                                sn[h] = __fma_rn(ts[idx], d, sn[h]);
+                            }
+                    }
+                }
+            }
+            double *ac = accs + (size_t)(warp * R + r) * nacc * 32 + lane;
+#pragma unroll
+            for (int h = 0; h < QL_NHMAX; h++)
+                if (h < nh) ac[(2 * h) * 32] += c[h], ac[(2 * h + 1) * 32] += sn[h];
+            ac[(2 * nh) * 32] += cnt;
+        }
+    };
+    // COEF: the time slice `row` is finished for this CTA: add its coefficients to the global arrays (a slice is
+    // shared with a neighbouring CTA at most at the two ends of this CTA's event range, hence the atomics)
+    auto flush_row = [&](int row) {
+        const int nh = a.nharm;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const long long c = (slot0 + r) * 32 + lane;
+            double *ac = accs + (size_t)(warp * R + r) * nacc * 32 + lane;
+            if (c < a.n_c) {
+                double *dst = a.coef + ((size_t)c * nprof + row) * nh * 2;
+                for (int k = 0; k < 2 * nh; k++) {
+                    const double v = ac[k * 32];
+                    if (v != 0.0) atomicAdd(dst + k, v);
+                }
+                const double n = ac[(2 * nh) * 32];
+                if (n != 0.0) atomicAdd(a.rowcnt + (size_t)c * nprof + row, (unsigned long long)n);
+            }
+            for (int k = 0; k < nacc; k++) ac[k * 32] = 0.0;
+        }
+    };
     auto one = [&](double t) {
         double h = 0.0, s6 = 0.0;
         if (MODE >= 1) {
@@ -442,6 +531,7 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
     int row = j0;                      // current row
     long long row_end = a.row_start[min(j0 + 1, nprof)];
     int since_drain = 0;
+    bool dirty = false;  // COEF: the accumulators hold part of the current row
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
         mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
@@ -451,7 +541,12 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
         int e = (int)max(0LL, ev_lo - s);  // only the first stage can start before ev_lo
         while (e < cnt) {
             while (s + e >= row_end && row < j1) {  // finished row(s): drain and advance (warp-uniform)
-                if (since_drain) drain(row), since_drain = 0;
+                if (COEF) {
+                    if (since_drain) accumulate(), since_drain = 0, dirty = true;
+                    if (dirty) flush_row(row), dirty = false;
+                } else if (since_drain) {
+                    drain(row), since_drain = 0;
+                }
                 row++;
                 row_end = a.row_start[min(row + 1, nprof)];
             }
@@ -460,7 +555,11 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             span(tp, e, e_end);
             since_drain += e_end - e;
             e = e_end;
-            if (PACKED && since_drain >= a.flush_events) drain(row), since_drain = 0;
+            if (PACKED && since_drain >= a.flush_events) {
+                if (COEF) accumulate(), dirty = true;
+                else drain(row);
+                since_drain = 0;
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -474,54 +573,16 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             }
         }
     }
-    if (since_drain) drain(min(row, nprof - 1));
-}
-
-// first event index of every row (binary search; the row index is monotone in t for sorted times)
-__global__ void qffa_rowstart_kernel(const double *__restrict__ t, long long n, double t_first, double delta1, int nprof,
-                                     long long *__restrict__ row_start) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > nprof) return;
-    // smallest e with jf(t[e]) >= j   (jf < 0 never happens for sorted t >= t_first)
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        const double jf = __dmul_rn(__dsub_rn(t[mid], t_first), delta1);
-        // row of mid: int(jf) if jf < nprof else "dropped" (counts as row nprof)
-        const bool before = (j == nprof) ? (jf < (double)nprof) : (jf < (double)j);
-        if (before) lo = mid + 1;
-        else hi = mid;
+    if (COEF) {
+        if (since_drain) accumulate(), dirty = true;
+        if (dirty) flush_row(min(row, nprof - 1));
+    } else if (since_drain) {
+        drain(min(row, nprof - 1));
     }
-    row_start[j] = lo;
-}
-
-// flag[0] = 1 if the times are not sorted ascending or not >= t_first
-__global__ void qffa_sorted_kernel(const double *__restrict__ t, long long n, double t_first, int *flag) {
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double v = t[i];
-        if (!(v >= t_first) || (i + 1 < n && t[i + 1] < v)) bad = true;
-    }
-    if (bad) atomicExch(flag, 1);
-}
-
-// [u0, u1) = events with |t| < t_safe (contiguous for sorted times)
-__global__ void qffa_unsafe_range_kernel(const double *__restrict__ t, long long n, double t_safe, long long *out) {
-    if (threadIdx.x > 1 || blockIdx.x > 0) return;
-    const double bound = threadIdx.x == 0 ? -t_safe : t_safe;
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        // u0: first t > -t_safe ; u1: first t >= t_safe
-        const bool before = threadIdx.x == 0 ? (t[mid] <= bound) : (t[mid] < bound);
-        if (before) lo = mid + 1;
-        else hi = mid;
-    }
-    out[threadIdx.x] = lo;
 }
 
 // Re-bin the photons with |t| < t_safe: remove the fast-path bin, add the reference's bin (if any).
-template <int MODE>
+template <int MODE, bool COEF = false>
 __global__ void __launch_bounds__(128) qffa_fix_kernel(const QLaneArgs a, const long long *__restrict__ urange,
                                                        double t_first, double delta0, double delta1) {
     const long long u0 = urange[0], u1 = urange[1];
@@ -546,9 +607,72 @@ __global__ void __launch_bounds__(128) qffa_fix_kernel(const QLaneArgs a, const 
         const int fast_bin = (int)(((uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC)) >> 7) & (uint32_t)(a.nbin - 1));
         const int ref_bin = qffa_bin_generic<MODE>(t, h, s6, f, fd, fdd, delta0, a.nbin);
         if (ref_bin == fast_bin) continue;
+        if (COEF) {  // move one count between bins in the harmonic domain: subtract the fast bin's rotation, add the right one
+            double *dst = a.coef + ((size_t)c * a.nprof + j) * a.nharm * 2;
+            for (int hh = 0; hh < a.nharm; hh++) {
+                const int i_f = ((hh + 1) * fast_bin) & (a.nbin - 1);
+                double dc = -a.tab[i_f], ds = -a.tab[a.nbin + i_f];
+                if (ref_bin >= 0) {
+                    const int i_r = ((hh + 1) * ref_bin) & (a.nbin - 1);
+                    dc += a.tab[i_r], ds += a.tab[a.nbin + i_r];
+                }
+                atomicAdd(dst + 2 * hh, dc);
+                atomicAdd(dst + 2 * hh + 1, ds);
+            }
+            if (ref_bin < 0) atomicAdd(a.rowcnt + (size_t)c * a.nprof + j, ~0ull);  // the reference drops this event
+            continue;
+        }
         uint32_t *p = a.prof + (((size_t)(c >> 5) * a.nprof + j) * a.nbin) * 32 + (c & 31);
         atomicSub(p + (size_t)fast_bin * 32, 1u);
         if (ref_bin >= 0) atomicAdd(p + (size_t)ref_bin * 32, 1u);
+    }
+}
+
+// COEF path: events folded per centre = sum of its slices' counts
+__global__ void qffa_tot_kernel(const unsigned long long *__restrict__ rowcnt, int n_c, int nprof,
+                                unsigned long long *__restrict__ tot) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= n_c) return;
+    unsigned long long sum = 0;
+    for (int k = lane; k < nprof; k += 32) sum += rowcnt[(size_t)c * nprof + k];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) tot[c] = sum;
+}
+
+// One pre-pass for the lane path: sortedness of the times (all threads), the first event of every time slice and the
+// [u0, u1) range of events with |t| < t_safe (binary searches by the first nprof + 3 threads).
+__global__ void qffa_prepass_kernel(const double *__restrict__ t, long long n, double t_first, double delta1, int nprof,
+                                    double t_safe, long long *__restrict__ row_start, long long *__restrict__ urange,
+                                    int *flag) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    for (long long i = gid; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = t[i];
+        if (!(v >= t_first) || (i + 1 < n && t[i + 1] < v)) bad = true;
+    }
+    if (bad) atomicExch(flag, 1);
+    if (gid <= nprof) {
+        const int j = (int)gid;  // smallest e with row(t[e]) >= j; row nprof = "dropped"
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            const double jf = __dmul_rn(__dsub_rn(t[mid], t_first), delta1);
+            const bool before = (j == nprof) ? (jf < (double)nprof) : (jf < (double)j);
+            if (before) lo = mid + 1;
+            else hi = mid;
+        }
+        row_start[j] = lo;
+    } else if (gid <= nprof + 2) {
+        const bool first = gid == nprof + 1;  // u0: first t > -t_safe ; u1: first t >= t_safe
+        const double bound = first ? -t_safe : t_safe;
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            const bool before = first ? (t[mid] <= bound) : (t[mid] < bound);
+            if (before) lo = mid + 1;
+            else hi = mid;
+        }
+        urange[first ? 0 : 1] = lo;
     }
 }
 
@@ -838,13 +962,18 @@ static double g_q_last_ms = -1.0;
 
 // ---- K2-lane host path -----------------------------------------------------------------------
 typedef void (*qlane_fn_t)(const QLaneArgs);
-template <int R, bool PACKED>
+template <int R, bool PACKED, bool COEF>
 static qlane_fn_t pick_qlane_m(int mode) {
-    return mode == 0 ? qffa_lane_kernel<R, 0, PACKED> : mode == 1 ? qffa_lane_kernel<R, 1, PACKED> : qffa_lane_kernel<R, 2, PACKED>;
+    return mode == 0 ? qffa_lane_kernel<R, 0, PACKED, COEF> : mode == 1 ? qffa_lane_kernel<R, 1, PACKED, COEF>
+                                                                      : qffa_lane_kernel<R, 2, PACKED, COEF>;
 }
-static qlane_fn_t pick_qlane(int R, int mode, bool packed) {
-    if (packed) return R == 4 ? pick_qlane_m<4, true>(mode) : R == 2 ? pick_qlane_m<2, true>(mode) : pick_qlane_m<1, true>(mode);
-    return R == 4 ? pick_qlane_m<4, false>(mode) : R == 2 ? pick_qlane_m<2, false>(mode) : pick_qlane_m<1, false>(mode);
+template <bool COEF>
+static qlane_fn_t pick_qlane_c(int R, int mode, bool packed) {
+    if (packed) return R == 4 ? pick_qlane_m<4, true, COEF>(mode) : R == 2 ? pick_qlane_m<2, true, COEF>(mode) : pick_qlane_m<1, true, COEF>(mode);
+    return R == 4 ? pick_qlane_m<4, false, COEF>(mode) : R == 2 ? pick_qlane_m<2, false, COEF>(mode) : pick_qlane_m<1, false, COEF>(mode);
+}
+static qlane_fn_t pick_qlane(int R, int mode, bool packed, bool coef) {
+    return coef ? pick_qlane_c<true>(R, mode, packed) : pick_qlane_c<false>(R, mode, packed);
 }
 
 static int g_qffa_lane = 1;  // tuning hook: 0 forces the lane = event kernel
@@ -891,12 +1020,12 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     HX_CUDA_TRY(cudaMemsetAsync(d_misc, 0, misc_bytes, st));
     long long *d_rowstart = reinterpret_cast<long long *>(d_misc), *d_urange = d_rowstart + nprof + 1;
     int *d_flags = reinterpret_cast<int *>(d_urange + 2);  // [0] unsorted, [1] layout error
-    qffa_sorted_kernel<<<(unsigned)std::min<long long>((n_ev + 255) / 256, 2368), 256, 0, st>>>(d_t, n_ev, t_first, d_flags);
-    HX_CHECK_LAUNCH("qffa_sorted_kernel");
-    qffa_rowstart_kernel<<<(nprof + 1 + 127) / 128, 128, 0, st>>>(d_t, n_ev, t_first, delta1, nprof, d_rowstart);
-    HX_CHECK_LAUNCH("qffa_rowstart_kernel");
-    qffa_unsafe_range_kernel<<<1, 32, 0, st>>>(d_t, n_ev, t_safe, d_urange);
-    HX_CHECK_LAUNCH("qffa_unsafe_range_kernel");
+    {
+        const long long want = std::max<long long>((n_ev + 255) / 256, (nprof + 3 + 255) / 256);
+        qffa_prepass_kernel<<<(unsigned)std::min<long long>(std::max<long long>(want, 1), 2368), 256, 0, st>>>(
+            d_t, n_ev, t_first, delta1, nprof, t_safe, d_rowstart, d_urange, d_flags);
+        HX_CHECK_LAUNCH("qffa_prepass_kernel");
+    }
     int h_flags[2] = {0, 0};
     long long h_urange[2] = {0, 0};
     HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
@@ -921,7 +1050,11 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     if (packed && foot == 64) R = 1, W = 2;  // nbin = 128 (the --fast default): many small CTAs, 16 resident warps
     // batches of equal size (multiples of 32 centres), bounded by 2 GiB of profile scratch (the whole C4 search -- 1252
     // centres, 1.25 GB -- is one batch: 38.2 -> 36.2 ms per search against three 512 MiB batches, profiles/r01_sweep_qbatch.txt)
-    const size_t per_centre = (size_t)nprof * nbin * 4;
+    // Fused path (no `profiles` output, nharm <= 4): a finished time slice is reduced in the SM to its 2 * nharm harmonic
+    // coefficients; the [slot][row][bin][32] count scratch (1 MB per centre at nbin = 128, nprof = 2048) does not exist.
+    bool coef_mode = d_profiles == nullptr && nharm >= 1 && nharm <= QL_NHMAX;
+    if (const char *e = getenv("HX_QFFA_FUSE")) coef_mode = coef_mode && atoi(e) != 0;  // tuning / A-B hook
+    const size_t per_centre = coef_mode ? (size_t)nprof * (2 * nharm + 1) * 8 : (size_t)nprof * nbin * 4;
     size_t batch_bytes = (size_t)2048 << 20;
     if (const char *e = getenv("HX_QFFA_BATCH_MIB")) {  // tuning hook
         const long long mib = atoll(e);
@@ -942,7 +1075,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         if (sscanf(e, "%d,%d", &r, &w) == 2 && (r == 1 || r == 2 || r == 4) && w >= 1 && w <= 16) R = r, W = w;
     }
     const uint32_t blk = (uint32_t)nbin * (packed ? 64u : 128u);
-    uint32_t hist_off, tile_off, total;
+    uint32_t hist_off, tile_off, total, extra_off = 0;
     int tile_ev = QL_TILE;
     for (;;) {
         const uint32_t hist_bytes = (uint32_t)W * R * blk;
@@ -959,18 +1092,22 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         const uint32_t tile_region = 2u * (uint32_t)(tile_ev + 16) * 8u;
         tile_off = fit ? 32u : hist_off + hist_bytes;
         total = std::max(hist_off + hist_bytes, tile_off + tile_region);
+        if (coef_mode) {  // tables + per-thread accumulators behind everything else
+            extra_off = (total + 15u) & ~15u;
+            total = extra_off + (2u * (uint32_t)nbin + (uint32_t)W * R * (2u * nharm + 1u) * 32u) * 8u;
+        }
         if (total <= (uint32_t)di.smem_optin) break;
         if (W > 1) W /= 2;
         else if (R > 1) R /= 2;
         else return 1;
     }
     const int ctas_per_sm = std::max(1, std::min(8, (int)(di.smem_per_sm / (total + di.reserved_smem))));
-    qlane_fn_t fn = pick_qlane(R, mode, packed);
+    qlane_fn_t fn = pick_qlane(R, mode, packed, coef_mode);
     HX_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
 
     const size_t lane_elems = (size_t)slots_max * nprof * nbin * 32;
     const size_t prof_elems = (size_t)nprof * nbin;
-    HX_CUDA_TRY(cudaMallocAsync(&d_lane, lane_elems * 4, st));
+    if (!coef_mode) HX_CUDA_TRY(cudaMallocAsync(&d_lane, lane_elems * 4, st));
     const size_t coef_elems = (size_t)cb_max * nprof * nharm * 2;
     HX_CUDA_TRY(cudaMallocAsync(&d_coef, coef_elems * 8 + (size_t)cb_max * 8 + (size_t)cb_max * nprof * 8, st));
     unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(d_coef) + coef_elems);
@@ -981,7 +1118,8 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     for (int64_t c0 = 0; c0 < n_centres; c0 += cb_max) {
         const int C = (int)std::min<int64_t>(cb_max, n_centres - c0);
         const int slots = (C + 31) / 32;
-        HX_CUDA_TRY(cudaMemsetAsync(d_lane, 0, (size_t)slots * nprof * nbin * 32 * 4, st));
+        if (coef_mode) HX_CUDA_TRY(cudaMemsetAsync(d_coef, 0, coef_elems * 8 + (size_t)cb_max * 8 + (size_t)cb_max * nprof * 8, st));
+        else HX_CUDA_TRY(cudaMemsetAsync(d_lane, 0, (size_t)slots * nprof * nbin * 32 * 4, st));
         QLaneArgs a{};
         a.t = d_t, a.n_ev = n_ev, a.row_start = d_rowstart;
         a.f = d_f + c0, a.fd = d_fd + c0, a.fdd = d_fdd + c0, a.n_c = C;
@@ -993,6 +1131,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         a.flush_events = (int)((1u << a.pack_shift) - 1u);
         a.prof = reinterpret_cast<uint32_t *>(d_lane);
         a.warps = W, a.hist_off = hist_off, a.tile_off = tile_off, a.tile_ev = tile_ev, a.errflag = d_flags + 1;
+        a.coef = reinterpret_cast<double *>(d_coef), a.rowcnt = d_rowcnt, a.tab = d_tab, a.nharm = nharm, a.extra_off = extra_off;
         const int grid_x = (slots + R * W - 1) / (R * W);
         const long long want_y = std::max<long long>(1, 4LL * di.sm_count * ctas_per_sm / grid_x);
         long long per = std::max<long long>((n_ev + want_y - 1) / want_y, 4LL * tile_ev);
@@ -1011,9 +1150,15 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         g_qev_batches++;
         if (n_unsafe > 0) {
             dim3 gf((unsigned)std::min<long long>(n_unsafe, 256), (unsigned)((C + 127) / 128));
-            if (mode == 0) qffa_fix_kernel<0><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
-            else if (mode == 1) qffa_fix_kernel<1><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
-            else qffa_fix_kernel<2><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            if (coef_mode) {
+                if (mode == 0) qffa_fix_kernel<0, true><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+                else if (mode == 1) qffa_fix_kernel<1, true><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+                else qffa_fix_kernel<2, true><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            } else {
+                if (mode == 0) qffa_fix_kernel<0><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+                else if (mode == 1) qffa_fix_kernel<1><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+                else qffa_fix_kernel<2><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
+            }
             HX_CHECK_LAUNCH("qffa_fix_kernel");
         }
         if (d_profiles) {
@@ -1021,12 +1166,17 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
                                                                  d_profiles + (size_t)c0 * prof_elems);
             HX_CHECK_LAUNCH("qffa_unlane_kernel");
         }
-        HX_CUDA_TRY(cudaMemsetAsync(d_tot, 0, (size_t)cb_max * 8, st));
-        dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)slots);
-        qffa_rowdft_lane_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
-            reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
-            transient_levels > 0 ? d_rowcnt : nullptr);
-        HX_CHECK_LAUNCH("qffa_rowdft_lane_kernel");
+        if (coef_mode) {
+            qffa_tot_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(d_rowcnt, C, nprof, d_tot);
+            HX_CHECK_LAUNCH("qffa_tot_kernel");
+        } else {
+            HX_CUDA_TRY(cudaMemsetAsync(d_tot, 0, (size_t)cb_max * 8, st));
+            dim3 g1((unsigned)((nprof + 7) / 8), (unsigned)slots);
+            qffa_rowdft_lane_kernel<<<g1, 256, 2 * (size_t)nbin * sizeof(double), st>>>(
+                reinterpret_cast<uint32_t *>(d_lane), C, nprof, nbin, nharm, d_tab, reinterpret_cast<double *>(d_coef), d_tot,
+                transient_levels > 0 ? d_rowcnt : nullptr);
+            HX_CHECK_LAUNCH("qffa_rowdft_lane_kernel");
+        }
         if (transient_levels > 0) {
             dim3 g3((unsigned)((nprof + 1 + 127) / 128), (unsigned)transient_levels, (unsigned)C);
             qffa_transient_kernel<<<g3, 128, 0, st>>>(reinterpret_cast<double *>(d_coef), d_rowcnt, nprof, transient_rows,

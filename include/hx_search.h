@@ -171,7 +171,8 @@ int hx_transient_search_dev(const double *d_times_c, int64_t n_ev, double t_firs
  * epoch_folding_search / z_n_search on them for the single trial (freq, fdot) (:297).
  *   times [n_ev] (as folding_orbital_search computes them: events.time - gti[0, 0]);  stats [n_t0];
  *   profiles [n_t0 * nbin] uint32 or NULL.  nharm == 0: epoch-folding chi^2, else Z^2_nharm.
- * sin() is CUDA's, not numpy's: statistics agree to ~1e-6 (isolated +-1 bin moves), not bit for bit. */
+ * sin() is CUDA's, not numpy's; measured: profiles identical to the reference arithmetic on all test cases
+ * (profiles/r02_orbital_diff.txt; a last-bit difference of sin almost never reaches a bin edge). */
 int hx_orbital_search(const double *times, int64_t n_ev, double freq, double fdot, double X, double Porb,
                       const double *T0, int64_t n_t0, int nbin, int nharm, double *stats, uint32_t *profiles,
                       int device);
@@ -181,12 +182,18 @@ int hx_orbital_search_dev(const double *d_times, int64_t n_ev, double freq, doub
 
 /* ---- K4: unbinned Z^2_n (extension; oracle formula hendrics/efsearch.py:366-404) ---------
  * stats[i*n_f + j] = 2/N * sum_{k=1..nharm} [(sum cos 2 pi k phi)^2 + (sum sin 2 pi k phi)^2]
- * with phi = frac(t*f + 0.5*t*t*fd) per event.
- */
+ * with phi = frac(t*f + 0.5*t*t*fd) per event, the phase rounded like the reference's fp64 phase
+ * (_pulse_phase_fast), one sin/cos per event*trial and the higher harmonics by angle addition.
+ * Limits: 1 <= nharm <= 8 (per-trial sums live in registers); |phase| < 2^48 cycles (HX_ERR_RANGE);
+ * non-finite inputs give HX_ERR_ARG; d_times 16-byte aligned.  Results are bit-reproducible from run
+ * to run (no floating-point atomics). */
 int hx_zn_unbinned(const double *times, int64_t n_ev, const double *freqs, int64_t n_f, const double *fdots,
                    int64_t n_fd, int nharm, double *stats, int device);
 int hx_zn_unbinned_dev(const double *d_times, int64_t n_ev, const double *d_freqs, int64_t n_f,
                        const double *d_fdots, int64_t n_fd, int nharm, double *d_stats, void *stream);
+/* measurement only: duration (ms) of the last K4 launch on the current device, and the FP64
+ * instructions it issues per event*trial */
+int hx_zn_last_kernel_ms(double *ms, int *fp64_ops_per_unit);
 
 /* ---- top-k candidates ----------------------------------------------------------------------
  * Replaces the argpartition branch of hendrics/base.py:1140-1146 (find_peaks_in_image):

@@ -47,6 +47,50 @@ def test_unbinned_known_answer():
     assert np.isclose(z[0], 2 * 3 * 1000)
 
 
+def test_unbinned_zn_event_splits_are_reproducible_and_negative_phases():
+    """Few trials -> the event list is split across CTAs and the partial sums are added in split order: two runs give
+    the same bits, and the result equals the oracle.  Negative fdots / times make the scaled phase negative (quadrant
+    bits of a two's-complement rint)."""
+    from hendrics_b200 import z_n_search_unbinned
+
+    ts = O.simulate_events(300001, 3000.0, seed=5) - 1500.0  # odd count, times on both sides of 0
+    freqs = np.array([9.9, 9.9009, 9.95])
+    fdots = np.array([-3e-6, 0.0, 1e-6])
+    ref = _unbinned_oracle(ts, freqs, fdots, 3)
+    a = z_n_search_unbinned(ts, freqs, nharm=3, fdots=fdots)[2]
+    b = z_n_search_unbinned(ts, freqs, nharm=3, fdots=fdots)[2]
+    assert np.array_equal(a, b)
+    np.testing.assert_allclose(a, ref, rtol=1e-9)
+
+
+def test_unbinned_zn_long_baseline_uses_the_reference_s_rounded_phase():
+    """T*f ~ 1e9 cycles: the fp64 phase carries ~1e-7 cycles of rounding noise, which the kernel must REPRODUCE (same
+    products, same sum) to stay within 1e-9 of the reference -- an exactly reduced phase would differ by ~1e-6."""
+    from hendrics_b200 import z_n_search_unbinned
+
+    ts = O.simulate_events(50000, 1e8, seed=9)
+    freqs = 9.9009 + 5e-9 * np.arange(64)
+    ref = _unbinned_oracle(ts, freqs, np.array([0.0]), 2)
+    _, got = z_n_search_unbinned(ts, freqs, nharm=2)
+    np.testing.assert_allclose(got, ref[0], rtol=1e-9)
+
+
+def test_unbinned_zn_argument_checks():
+    from hendrics_b200 import _cabi, z_n_search_unbinned
+
+    ts = np.arange(100.0)
+    with pytest.raises(_cabi.HxError, match="nharm"):
+        z_n_search_unbinned(ts, np.array([1.0]), nharm=9)
+    with pytest.raises(_cabi.HxError):
+        z_n_search_unbinned(np.array([0.0, np.nan, 2.0]), np.array([1.0]), nharm=2)
+    with pytest.raises(_cabi.HxError, match="range"):
+        z_n_search_unbinned(ts * 1e13, np.array([10.0]), nharm=2)
+    ms, ops = None, None
+    z_n_search_unbinned(ts, np.array([1.0, 2.0]), nharm=2, fdots=[0.0, 1e-9])
+    ms, ops = _cabi.zn_last_kernel()
+    assert ms > 0 and ops == 8 + 16 + 4 + 4
+
+
 def test_topk_matches_oracle():
     import ctypes
 
