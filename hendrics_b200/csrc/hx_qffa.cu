@@ -510,11 +510,28 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             else red_shared_inc((lo & mask) | cb[r]);
         }
     };
-    // plain events [b, e) of a stage: K1's straight-line loop
+    // bin address (and packed increment) of event t for centre r
+    auto addr = [&](double t, int r, uint32_t &inc) -> uint32_t {
+        double x = __dmul_rn(t, fN[r]);
+        if (MODE >= 1) {
+            const double tssq = __dmul_rn(t, t);
+            x = __dadd_rn(x, __dmul_rn(__dmul_rn(0.5, tssq), fdN[r]));
+            if (MODE >= 2) x = __dadd_rn(x, __dmul_rn(__dmul_rn(__dmul_rn(1.0 / 6, tssq), t), fddN[r]));
+        }
+        const uint32_t lo = (uint32_t)__double2loint(__dadd_rd(x, HX_MAGIC));
+        inc = PACKED ? ((lo & topbit) | 1u) : 1u;
+        return (lo & mask) | cb[r];
+    };
+    // plain events [b, e) of a stage.  K1's skewed software pipeline: the bin addresses of group g + 1 are computed (FP64
+    // pipe) while the increments of group g are issued (shared-memory pipe), so the two interleave finely.
     auto span = [&](const unsigned char *tp, int b, int e) {
         int i = b;
         if ((i & 1) && i < e) one(*reinterpret_cast<const double *>(tp + (size_t)i * 8)), i++;
-        if (i + UE <= e) {
+        // measured on B200 (profiles/r02_sweep_qlane_fused_skew.txt): the skew pays for R <= 2 (+10 % at nbin = 64, +6 % at
+        // nbin = 128 R = 2) and costs registers for R = 4 (-20 % at nbin = 16), which keeps the straight loop
+        constexpr bool SKEW = R <= 2;
+        const int ngroups = SKEW ? (e - i) / UE : 0;
+        if (!SKEW && i + UE <= e) {
             double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8);
             double2 v1 = *reinterpret_cast<const double2 *>(tp + (size_t)i * 8 + 16);
             for (; i + UE <= e; i += UE) {
@@ -524,6 +541,33 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
                 one(v0.x), one(v0.y), one(v1.x), one(v1.y);
                 v0 = n0, v1 = n1;
             }
+        }
+        if (ngroups > 0) {
+            uint32_t ad_cur[UE * R], inc_cur[UE * R], ad_nxt[UE * R], inc_nxt[UE * R];
+            double tc[UE], tn[UE];
+            auto load4 = [&](double *dst, int at) {  // may read the 16-event pad after the stage; unused then
+                const double2 v0 = *reinterpret_cast<const double2 *>(tp + (size_t)at * 8);
+                const double2 v1 = *reinterpret_cast<const double2 *>(tp + (size_t)at * 8 + 16);
+                dst[0] = v0.x, dst[1] = v0.y, dst[2] = v1.x, dst[3] = v1.y;
+            };
+            load4(tc, i);
+            load4(tn, i + UE);
+#pragma unroll
+            for (int k = 0; k < UE * R; k++) ad_cur[k] = addr(tc[k / R], k % R, inc_cur[k]);
+            for (int g = 0; g < ngroups; g++) {
+#pragma unroll
+                for (int u = 0; u < UE; u++) tc[u] = tn[u];
+                load4(tn, i + (g + 2) * UE);
+#pragma unroll
+                for (int k = 0; k < UE * R; k++) {
+                    ad_nxt[k] = addr(tc[k / R], k % R, inc_nxt[k]);  // group g + 1 (garbage after the last group: never issued)
+                    if (PACKED) red_shared_add_u32(ad_cur[k], inc_cur[k]);
+                    else red_shared_inc(ad_cur[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < UE * R; k++) ad_cur[k] = ad_nxt[k], inc_cur[k] = inc_nxt[k];
+            }
+            i += ngroups * UE;
         }
         for (; i < e; i++) one(*reinterpret_cast<const double *>(tp + (size_t)i * 8));
     };
@@ -1047,7 +1091,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     int R = foot <= 32 ? 4 : foot <= 64 ? 2 : 1;
     if (mode >= 1 && R == 4 && foot > 16) R = 2;
     int W = foot <= 16 ? 2 : 4;
-    if (packed && foot == 64) R = 1, W = 2;  // nbin = 128 (the --fast default): many small CTAs, 16 resident warps
+    if (packed && foot == 64) R = 2, W = 4;  // nbin = 128 (the --fast default): 12 resident warps, half the event loads per unit
     // batches of equal size (multiples of 32 centres), bounded by 2 GiB of profile scratch (the whole C4 search -- 1252
     // centres, 1.25 GB -- is one batch: 38.2 -> 36.2 ms per search against three 512 MiB batches, profiles/r01_sweep_qbatch.txt)
     // Fused path (no `profiles` output, nharm <= 4): a finished time slice is reduced in the SM to its 2 * nharm harmonic
