@@ -39,7 +39,7 @@ METRIC = "Z_n^2 / epoch-folding search throughput (event*trials/s)"
 UNIT = "event*trials/s"
 
 # fixed frequency-grid width of the strong-scaling mode (split over the ranks); weak mode: n_freq per GPU below
-STRONG_N_FREQ = {"c1": 10_000, "c2": 1_000_000, "c3": 16_384, "c5": 32_768}
+STRONG_N_FREQ = {"c1": 10_000, "c2": 1_000_000, "c3": 16_384, "c5": 100_000}
 
 # name -> (description, n_events, T, n_freq per GPU, f_start, f_step, n_fdot, fdot0, fdot_step, nbin, nharm, seed)
 WORKLOADS = {
@@ -50,8 +50,9 @@ WORKLOADS = {
     "c3": ("C3 slab: Z^2_4 nbin=128, 1e7 events x 64 fdots x a slab of the 1e6-frequency grid "
            "(full config: all 1e6 frequencies sharded over 8 GPUs)",
            10_000_000, 1e5, 2048, 7.4, 5e-6, 64, -1.6e-9, 5e-11, 128, 4, 3),
-    "c5": ("C5 slice: Z^2_2 nbin=128, long baseline 1e8 s, 2e7 events x 4096 frequencies per GPU",
-           20_000_000, 1e8, 4096, 9.9009, 5e-9, 1, 0.0, 0.0, 128, 2, 5),
+    "c5": ("C5: Fermi-like long baseline, Z^2_2 nbin=128, 1e8 events over 1e8 s x 1e5 trial frequencies at step 1/(2T) "
+           "(the whole config; weak mode: 12500 frequencies per GPU)",
+           100_000_000, 1e8, 12_500, 9.9009, 5e-9, 1, 0.0, 0.0, 128, 2, 5),
 }
 
 
@@ -67,7 +68,7 @@ def algorithmic_ops_per_evtr(n_fd_nonzero):
 
 
 def default_scaling(wl):
-    return "strong" if wl == "c3" else "weak"
+    return "strong" if wl in ("c3", "c5") else "weak"
 
 
 def make_inputs(wl, rank, world, scaling="weak"):
