@@ -785,6 +785,7 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         }
         for (int W = 1; W <= 16; W++) {
             FoldPlan p;
+            if (W == 3 || (W > 4 && W % 4 != 0)) continue;  // keep the SM's four schedulers evenly loaded
             if (!plan_layout(di, nbin, R, W, mode, regs, use_m2t(R), &p)) continue;
             int res = p.ctas_per_sm * W;
             if (res > best_res) best = p, best_res = res;
@@ -800,13 +801,36 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
     long long n_tb_row = (n_f + 32LL * R - 1) / (32LL * R);
     long long n_tb = rowfd ? n_tb_row * n_fd : (n_trials + 32LL * R - 1) / (32LL * R);  // 32*R-trial blocks
     int W = best.W;
-    // few trials: shrink CTAs so that every SM gets one, then split the events across CTAs
+    // Few trial blocks: either shrink the CTAs so that every SM gets one, or keep the preferred shape and let the event
+    // splitting below multiply the CTAs.  Small CTAs cost resident warps (the stage buffers are per CTA), splitting needs
+    // enough events: score both (wave efficiency after the best split x resident warps relative to the preferred plan)
+    // and keep the better one.  (C5 strong scaling, 12 500 f per GPU: W = 2 ran 10 warps per SM, W = 4 + splits runs 12.)
     {
         long long want = (n_tb + di.sm_count - 1) / di.sm_count;
         if (want < W) {
+            // warps per CTA that keep the four schedulers of an SM evenly loaded: 1, 2 or a multiple of 4 (3- and 6-warp
+            // CTAs measured 15-30 % slower in every sweep: profiles/r01_sweep_m2t.txt, r02_sweep_qlane_fused_skew.txt)
             int Wn = (int)std::max<long long>(1, want);
-            FoldPlan p;
-            if (plan_layout(di, nbin, R, Wn, mode, regs, m2t, &p)) best = p, W = Wn;
+            if (Wn == 3) Wn = 4;
+            else if (Wn > 4) Wn = (Wn + 3) / 4 * 4;
+            FoldPlan pn;
+            if (Wn < W && plan_layout(di, nbin, R, Wn, mode, regs, m2t, &pn)) {
+                const double warps_pref = (double)best.ctas_per_sm * W;
+                auto score_of = [&](const FoldPlan &pl, int Wc) {
+                    const long long ncx = (n_tb + Wc - 1) / Wc, sl = (long long)di.sm_count * pl.ctas_per_sm;
+                    const long long s_max = n_ev > 0 ? std::min<long long>(std::max<long long>(1, n_ev / std::max(4 * pl.tile_ev, 8192)), 4096) : 1;
+                    double b = 0.0;
+                    for (long long sp = 1; sp <= s_max; sp++) {
+                        const double waves = (double)(ncx * sp) / (double)sl;
+                        const double sc = waves / std::ceil(waves) * (1.0 - 0.04 / std::max(waves, 1.0)) /
+                                          (1.0 + 4.0 * nbin * (double)sp / (double)std::max<int64_t>(n_ev, 1));
+                        b = std::max(b, sc);
+                        if (waves >= 16.0) break;
+                    }
+                    return b * std::min(1.0, (double)pl.ctas_per_sm * Wc / warps_pref);
+                };
+                if (score_of(pn, Wn) > score_of(best, W)) best = pn, W = Wn;
+            }
         }
     }
     if (m2t) {  // whole CTAs per fdot row: the fdot-term tile of a CTA is for ONE fdot
@@ -836,7 +860,9 @@ int fold_search_dev_impl(const double *d_times, int64_t n_ev, const double *d_fr
         double best_score = -1.0;
         for (long long sp = 1; sp <= s_max; sp++) {
             const double waves = (double)(n_cta_x * sp) / (double)slots;
-            const double eff = waves / std::ceil(waves);
+            // a single wave cannot overlap the CTAs' prologues / drains with other CTAs' folding (measured on the C5 shape:
+            // 1 wave 0.953, 2 waves 0.975, 4 waves 0.977 of the many-wave rate): mild preference for more waves
+            const double eff = waves / std::ceil(waves) * (1.0 - 0.04 / std::max(waves, 1.0));
             const double penalty = 1.0 + ((sp > 1 || must_scratch) ? 4.0 * nbin * (double)sp / (double)n_ev : 0.0);
             const double score = eff / penalty;
             if (score > best_score * 1.01) best_score = score, ev_splits = sp;

@@ -1113,6 +1113,8 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         // CTA columns: as few as possible, each with just enough warps for its share of the slots
         const int gx = (slots_max + R * W - 1) / (R * W);
         W = std::max(1, (slots_max + R * gx - 1) / (R * gx));
+        if (W == 3) W = 4;  // 1, 2 or a multiple of 4 warps: 3- and 6-warp CTAs load the SM's four schedulers unevenly
+        else if (W > 4) W = (W + 3) / 4 * 4;
     }
     if (const char *e = getenv("HX_QLANE_RW")) {  // tuning hook: "R,W"
         int r = 0, w = 0;
