@@ -170,3 +170,29 @@ def test_qffa_profile_batches_are_transparent(monkeypatch):
     s_many, p_many = _host_qffa(ts, cents, 32, 256, L, Q, 2)
     assert np.array_equal(p_one, p_many)
     assert np.array_equal(s_one, s_many)
+
+
+@pytest.mark.parametrize("nbin,nprof,n,mode,n_ev", [(128, 2048, 2, 0, 300_000), (128, 8, 4, 1, 400_000), (64, 512, 1, 2, 200_000),
+                                                    (16, 64, 3, 0, 50_001), (32, 4, 2, 1, 1_000_000), (128, 256, 5, 0, 60_000)])
+def test_fused_coefficient_drain_equals_the_profile_path(nbin, nprof, n, mode, n_ev):
+    """Without a `profiles` output K2 reduces every finished time slice in the SM to its harmonic coefficients (fp64
+    accumulators, packed counters emptied several times per slice, slices shared between CTAs through fp64 REDs); with
+    one, the counts go to the global scratch and K3a computes the same coefficients from it.  Same statistics either
+    way (the summation order differs: 1e-12), and both within 1e-9 of the oracle's shift-and-sum on the bit-exact
+    profiles.  nprof = 4 / 8 with 1e6 / 4e5 events puts several CTAs on every slice; n = 5 exceeds the fused path's
+    harmonics and takes the scratch path on both sides."""
+    from hendrics_b200.efsearch import _qffa_device_call, _shift_grids, _to_device
+
+    ts = _centred(n_ev, 5000.0, seed=nbin + nprof)
+    cents = [(9.9 + 0.0007 * k, (3e-8 if mode >= 1 else 0.0) * (k % 3), (2e-12 if mode >= 2 else 0.0)) for k in range(70)]
+    L, Q = _shift_grids(nbin, 2, 4, True)
+    td = _to_device(ts)
+    fused = _qffa_device_call(td, ts[0], ts[-1], cents, nbin, nprof, L, Q, n)
+    scratch, prof = _qffa_device_call(td, ts[0], ts[-1], cents, nbin, nprof, L, Q, n, want_profiles=True)
+    np.testing.assert_allclose(fused, scratch, rtol=1e-12, atol=1e-12 * np.abs(scratch).max())
+    again = _qffa_device_call(td, ts[0], ts[-1], cents, nbin, nprof, L, Q, n)
+    np.testing.assert_allclose(again, fused, rtol=1e-13, atol=1e-13 * np.abs(fused).max())
+    for k in (0, 33, 69):
+        ref_p = C.qffa_profiles(ts, *cents[k], nbin, nprof)
+        assert np.array_equal(prof[k].astype(np.uint64), ref_p)
+        np.testing.assert_allclose(fused[k], C.fast_step(ref_p, L, Q, n), rtol=RTOL)
