@@ -261,6 +261,7 @@ def run_c4(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from hendrics_b200 import _cabi
+    from hendrics_b200 import dist as hdist
     from hendrics_b200.efsearch import _qffa_device_call
 
     desc, tc, cents, L, Q, nbin, nprof, n = c4_inputs(rank, world)
@@ -308,8 +309,10 @@ def run_c4(args):
 
     # e2e: host array in (H2D of the 0.8 GB event list every step), host stats out
     pin = torch.from_numpy(tc).pin_memory()
+    pin_np = pin.numpy()
     def step_e2e():
-        d = pin.to(dev, non_blocking=True)
+        # what search_with_qffa does: N ranks upload 1/N of the (replicated) list each + one NVLink all-gather
+        d = hdist.upload_replicated(pin_np)
         return _qffa_device_call(d, tc[0], tc[-1], cents, nbin, nprof, L, Q, n)
     step_e2e()
     barrier()

@@ -11,7 +11,11 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["rank", "world_size", "shard_bounds", "all_gather_concat", "sharded_search", "sharded_rows"]
+__all__ = ["rank", "world_size", "shard_bounds", "all_gather_concat", "sharded_search", "sharded_rows",
+           "upload_replicated"]
+
+# Host arrays at least this large are uploaded in shards (see upload_replicated); smaller ones are not worth a collective
+REPLICATED_UPLOAD_MIN_BYTES = 32 << 20
 
 
 def _dist():
@@ -85,6 +89,44 @@ def all_gather_concat(local, counts, axis=-1):
     return np.moveaxis(_to_host(out), -1, axis)
 
 
+def upload_replicated(a, device=None, min_bytes=None):
+    """Host fp64 array that is IDENTICAL on every rank (the replicated event list) -> device tensor on every rank.
+
+    One process: a plain H2D copy.  Several NCCL ranks and a large array: every rank copies only ITS 1/N of the array
+    over its own PCIe link and one NVLink all-gather assembles the whole list on every GPU -- 8 x 0.1 GB of H2D in
+    parallel plus ~2 ms of NVSwitch traffic instead of 8 concurrent 0.8 GB copies out of the same host memory (measured
+    on C4 / C5 at 8 GPUs: the replicated copies took 30-50 ms per step).  The ranks first agree that they hold the
+    same array (size, ends, a strided checksum): a mismatch raises on every rank instead of silently mixing inputs.
+    Collective: every rank must call it."""
+    import torch
+
+    from .search import _device
+
+    dev = _device(device)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    limit = REPLICATED_UPLOAD_MIN_BYTES if min_bytes is None else min_bytes
+    if not is_distributed() or _dist().get_backend() != "nccl" or a.nbytes < limit:
+        return torch.from_numpy(a).to(dev)
+    d = _dist()
+    ws, r = d.get_world_size(), d.get_rank()
+    probe = a[:: max(1, a.size // 4096)]
+    sig = torch.tensor(np.nan_to_num([float(a.size), float(a[0]), float(a[-1]), float(probe.sum())]), dtype=torch.float64,
+                       device=dev)
+    both = torch.cat([sig, -sig])
+    d.all_reduce(both, op=d.ReduceOp.MAX)  # max(x) and -min(x) in one collective
+    if not torch.equal(both[:4], -both[4:]):
+        raise ValueError("upload_replicated: the ranks hold different arrays (size / ends / checksum differ)")
+    per = (a.size + ws - 1) // ws
+    per += per & 1  # even: every shard starts 16-byte aligned
+    lo, hi = min(a.size, r * per), min(a.size, (r + 1) * per)
+    mine = torch.zeros(per, dtype=torch.float64, device=dev)
+    if hi > lo:
+        mine[: hi - lo].copy_(torch.from_numpy(a[lo:hi]), non_blocking=False)
+    full = torch.empty(per * ws, dtype=torch.float64, device=dev)
+    d.all_gather_into_tensor(full, mine)
+    return full[: a.size]
+
+
 def _raise_together(err):
     """One rank failing (e.g. HxRangeError for its slice) must not leave the others blocked in the all-gather:
     agree on an error flag first and raise on every rank."""
@@ -126,6 +168,13 @@ def sharded_search(func, times, trial_freqs, fdots=0, **kwargs):
     lo, hi = bounds[r]
     if getattr(func, "_hx_device_stats", False) and _dist().get_backend() == "nccl":
         kwargs = dict(kwargs, _device_stats=True)
+        from .search import _is_slow_branch
+
+        t_np = np.asanyarray(times)
+        if (t_np.dtype == np.float64 and t_np.ndim == 1 and t_np.nbytes >= REPLICATED_UPLOAD_MIN_BYTES
+                and not _is_slow_branch(kwargs.get("expocorr", False), kwargs.get("weights", 1))):
+            # the event list is the same on every rank: upload 1/N each, all-gather over NVLink
+            times = _call_local(lambda: upload_replicated(t_np))
     res = _call_local(lambda: func(times, trial_freqs[lo:hi], fdots=fdots, **kwargs))
     fd = np.atleast_1d(np.asarray(fdots, dtype=np.float64))
     local = res[-1]

@@ -69,11 +69,11 @@ class CentredTimes:
         return self.times[-1]
 
     def on_device(self):
-        import torch
+        """The searches that use this are collective when torch.distributed is initialised (centres sharded over the
+        ranks): the replicated event list goes up in shards + one NVLink all-gather (dist.upload_replicated)."""
+        from .dist import upload_replicated
 
-        from .search import _device
-
-        return torch.from_numpy(np.ascontiguousarray(self.times)).to(_device(None))
+        return upload_replicated(self.times)
 
 
 def centre_ladder(f0, f1, step):

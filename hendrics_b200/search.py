@@ -156,11 +156,27 @@ def _folding_search(
     frequencies = np.atleast_1d(np.asanyarray(frequencies).astype(np.float64))
     fdots = np.atleast_1d(np.asanyarray(fdots).astype(np.float64))
     grid_shape = (fdots.size, frequencies.size)
-    times = np.asanyarray(times)
-    if times.size == 0:
-        raise ValueError("No events to fold")
     rezero = UPSTREAM_SEMANTICS["rezero_to_first_event"]
-    if times.dtype == np.float64:
+    if isinstance(times, torch.Tensor):
+        # already on the device (dist.upload_replicated: sharded H2D + NVLink all-gather of the replicated event list)
+        if times.dtype != torch.float64 or times.dim() != 1:
+            raise TypeError("device event lists must be 1-D float64 tensors")
+        if times.numel() == 0:
+            raise ValueError("No events to fold")
+        times_d = times.to(dev)
+        ends = times_d[[0, -1]].cpu().numpy()
+        t_first = np.float64(ends[0] - ends[0]) if rezero else np.float64(ends[0])
+        length = np.float64(ends[1] - ends[0]) if rezero else np.float64(ends[1])
+        if rezero:
+            times_d = times_d - float(ends[0])
+        times = None
+    else:
+        times = np.asanyarray(times)
+        if times.size == 0:
+            raise ValueError("No events to fold")
+    if times is None:
+        pass
+    elif times.dtype == np.float64:
         # A1: re-zero to the first event.  The fp64 subtraction is done on the device (same IEEE
         # operation as numpy's) to spare two host passes over the event list.
         t_first = np.float64(times[0] - times[0]) if rezero else np.float64(times[0])

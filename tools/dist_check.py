@@ -32,8 +32,26 @@ assert np.array_equal(wfull[1], wref[1]), np.abs(wfull[1] - wref[1]).max()
 xfull = folding_search(ev, 9.85, 9.95, func=z_n_search, oversample=2, nbin=64, nharm=2, expocorr=True)
 xref = z_n_search(t, xfull[0], nharm=2, nbin=64, expocorr=True, gti=(ev.gti - 8e7).astype(np.float64))
 assert np.array_equal(xfull[1], xref[1])
+# the replicated event list goes up in shards + one NVLink all-gather: same bits on every rank, ragged sizes included
+for n in (1, 7, 1000, 50001, 1 << 20):
+    a = np.random.default_rng(n).uniform(0, 1e5, n)
+    got = hd.upload_replicated(a, min_bytes=0)
+    assert got.shape == (n,) and np.array_equal(got.cpu().numpy(), a), n
+bad = np.arange(1000.0) + (1.0 if dist.get_rank() == 1 else 0.0)
+try:
+    hd.upload_replicated(bad, min_bytes=0)
+    raise SystemExit("upload_replicated accepted different arrays")
+except ValueError:
+    pass
+hd.REPLICATED_UPLOAD_MIN_BYTES = 0  # force the sharded upload inside the searches below
+again = folding_search(ev, 9.85, 9.95, func=z_n_search, oversample=2, nbin=64, nharm=2, fdotmin=-1e-6, fdotmax=1e-6)
+assert np.array_equal(again[2], full[2])
 np.random.seed(0)
 q = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, silent=True)
+np.random.seed(0)
+hd.REPLICATED_UPLOAD_MIN_BYTES = 32 << 20
+q2 = search_with_qffa(ts, 9.85, 9.95, nbin=16, n=2, silent=True)
+assert np.array_equal(q[2], q2[2])
 os.environ["HX_NO_SHARD"] = "1"
 print(f"rank {dist.get_rank()}: sharded search ok, stats {full[2].shape}, qffa {q[2].shape}, best f {full[0].flat[np.argmax(full[2])]:.4f}", flush=True)
 dist.barrier()
