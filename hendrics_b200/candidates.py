@@ -211,8 +211,9 @@ class CandTable:
 # ---------------------------------------------------------------------------------------------
 def get_boundaries_from_level(x, y, level, x0):
     """Extent of the region around ``x0`` where ``y`` stays above ``level`` (hendrics/efsearch.py:1299-1332): walk
-    outwards from the sample nearest to ``x0`` while ``y > level``; the last sample still above it is the limit.
-    (The reference indexes one past the end when the region touches the right edge; here it stops at the edge.)
+    outwards from the sample nearest to ``x0`` while ``y > level``; the last sample still above it is the limit (the
+    first sample is never tested on the way down, like in the reference's ``while idx > 0``).  Pinned to the reference's
+    own function on 64 seeded cases (tests/golden/boundaries.npz).
 
     >>> x = np.linspace(-10, 10, 1000)
     >>> y = np.sinc(x)**2 + np.sinc((x - 5))**2

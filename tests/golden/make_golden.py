@@ -197,6 +197,29 @@ def main():
     out["ffa_events_nbin24"] = dict(times=ts[:6000], params=np.array([3.1, 3.4, 24, 1]), freqs=np.asarray(res[0]),
                                     stats=np.asarray(res[1]), length=np.array([res[3]]))
 
+    # ---- 9. candidate post-processing (in-tree, numpy only: efsearch.py:1299-1332, 208-260) -------------------
+    rng = np.random.default_rng(9)
+    bx, by, blevel, bx0, bout = [], [], [], [], []
+    for k in range(64):
+        n = int(rng.integers(1, 60))
+        x = np.sort(rng.uniform(-5, 5, n))
+        y = rng.uniform(0, 1, n) if k % 4 else np.sinc(x) ** 2 + np.sinc(x - 2.5) ** 2
+        level, x0 = float(rng.uniform(0, 1)), float(rng.uniform(-6, 6))
+        lo, hi = hef.get_boundaries_from_level(x, y, level, x0)
+        bx.append(np.pad(x, (0, 60 - n))), by.append(np.pad(y, (0, 60 - n)))
+        blevel.append([n, level, x0]), bout.append([lo, hi])
+    out["boundaries"] = dict(x=np.array(bx), y=np.array(by), params=np.array(blevel), out=np.array(bout))
+    import tempfile
+
+    np.random.seed(9)
+    csv = os.path.join(tempfile.mkdtemp(), "db.csv")
+    hef.decide_binary_parameters(137430, [0.03, 0.035], [2.0 * 86400, 2.5 * 86400], [0.0, 1.0], fdot_range=[0, 5e-10],
+                                 NMAX=3, csv_file=csv, reset=True)
+    import pandas as pd
+
+    df = pd.read_csv(csv)
+    out["binary_parameters"] = dict(table=df[["freq", "fdot", "X", "Porb"]].to_numpy(dtype=np.float64))
+
     only = sys.argv[1] if len(sys.argv) > 1 else ""  # `make_golden.py ffa`: (re)write only the fixtures with that prefix
     for name, d in out.items():
         if name.startswith(only):

@@ -246,3 +246,31 @@ def test_orbital_extremes_follow_the_running_max_min():
     assert _extremes(T0, [1.0, 5.0, 5.0, np.nan]) == (5.0, 1.0, 20.0)  # first of equal maxima, NaN never wins
     assert _extremes(T0, [np.nan] * 4) == (0, 1e32, None)
     assert _extremes(T0, [0.0, -1.0, 0.0, 0.0]) == (0, -1.0, None)
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_boundaries_golden_from_the_real_reference():
+    """tests/golden/boundaries.npz: 64 seeded cases run through the reference's own get_boundaries_from_level
+    (hendrics/efsearch.py:1299-1332, executed by make_golden.py): identical limits."""
+    g = np.load(os.path.join(GOLD, "boundaries.npz"))
+    for x, y, (n, level, x0), ref in zip(g["x"], g["y"], g["params"], g["out"]):
+        n = int(n)
+        assert get_boundaries_from_level(x[:n], y[:n], level, x0) == tuple(ref)
+
+
+def test_binary_parameter_table_golden_from_the_real_reference(tmp_path):
+    """tests/golden/binary_parameters.npz: the reference's decide_binary_parameters (hendrics/efsearch.py:208-260) with
+    numpy's global RNG seeded: the restructured generator draws the same numbers in the same order."""
+    import pandas as pd
+
+    from hendrics_b200.orbital import PARAMETER_COLUMNS, decide_binary_parameters
+
+    np.random.seed(9)
+    csv = decide_binary_parameters(137430, [0.03, 0.035], [2.0 * 86400, 2.5 * 86400], [0.0, 1.0], fdot_range=[0, 5e-10],
+                                   NMAX=3, csv_file=str(tmp_path / "db.csv"), reset=True)
+    df = pd.read_csv(csv)
+    assert list(df.columns) == PARAMETER_COLUMNS and not df["done"].any()
+    ref = np.load(os.path.join(GOLD, "binary_parameters.npz"))["table"]
+    assert np.array_equal(df[["freq", "fdot", "X", "Porb"]].to_numpy(dtype=np.float64), ref)
