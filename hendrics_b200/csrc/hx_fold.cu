@@ -45,6 +45,9 @@ namespace hx {
 #ifndef HX_FOLD_SKEW_FD
 #define HX_FOLD_SKEW_FD 0  // 1: skewed software pipeline for the (f, fdot) kernels too (measured on B200: no gain, C3 3.21e12 either way)
 #endif
+#ifndef HX_FOLD_HYB
+#define HX_FOLD_HYB 0  // M2T experiment: of every group of UE events, the fdot term of the last HX_FOLD_HYB is recomputed per thread
+#endif                 // (2 FP64 ops per event and thread) instead of loaded from the tile (one broadcast wavefront per event and warp)
 #ifndef HX_FOLD_SKEW_UE2
 #define HX_FOLD_SKEW_UE2 4  // events per register group of the skewed (f, fdot) loop with 2 trials per thread
 #endif
@@ -172,6 +175,24 @@ struct EvGroup {
                 double2 v = *reinterpret_cast<const double2 *>(mp + (size_t)(e + u) * 8);
                 m2[u] = v.x, m2[u + 1] = v.y;
             }
+        }
+    }
+    // hybrid M2T: load the terms of the first n_load events of the group, recompute the others
+    __device__ __forceinline__ void load_m2_n(const unsigned char *mp, int e, int n_load) {
+        if (HAS_FD) {
+#pragma unroll
+            for (int u = 0; u < UE; u += 2)
+                if (u < n_load) {
+                    double2 v = *reinterpret_cast<const double2 *>(mp + (size_t)(e + u) * 8);
+                    m2[u] = v.x, m2[u + 1] = v.y;
+                }
+        }
+    }
+    __device__ __forceinline__ void squares_from(double fdH_row, int from) {
+        if (HAS_FD) {
+#pragma unroll
+            for (int u = 0; u < UE; u++)
+                if (u >= from) m2[u] = __dmul_rn(__dmul_rn(t[u], t[u]), fdH_row);
         }
     }
     // fdH_row: the thread's fdot constant when all its trials share it (ROWFD), else unused
@@ -410,7 +431,8 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
         if (M2T) cur.load_m2(mp, 0);
         for (; e + UE <= cnt; e += UE) {
             nxt.load(tp, e + UE);  // may read the pad after the stage; never used past cnt
-            if (M2T) nxt.load_m2(mp, e + UE);
+            if (M2T && HX_FOLD_HYB > 0 && HX_FOLD_HYB < UE) nxt.load_m2_n(mp, e + UE, UE - HX_FOLD_HYB), cur.squares_from(fdH_row, UE - HX_FOLD_HYB);
+            else if (M2T) nxt.load_m2(mp, e + UE);
             else cur.squares(fdH_row);
 #pragma unroll
             for (int u = 0; u < UE; u++) {
@@ -427,7 +449,7 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
 #pragma unroll
             for (int u = 0; u < UE; u++) {
                 cur.t[u] = nxt.t[u];
-                if (M2T) cur.m2[u] = nxt.m2[u];
+                if (M2T && u < UE - HX_FOLD_HYB) cur.m2[u] = nxt.m2[u];
             }
         }
         }
