@@ -296,7 +296,8 @@ struct QLaneArgs {
     unsigned long long *rowcnt;   // [n_c][nprof] events of the slice
     const double *tab;            // [2 * nbin] cos | sin (global); staged at extra_off
     int nharm;                    // <= QL_NHMAX
-    uint32_t extra_off;           // tables [2 * nbin] then accumulators [warps * R][2 * nharm + 1][32] (doubles)
+    uint32_t extra_off;           // the staged tables
+    int rows_per_cta;             // > 0: CTA y folds the time slices [y * rows_per_cta, (y + 1) * rows_per_cta) and nothing else
 };
 constexpr int QL_NHMAX = 4;
 
@@ -318,13 +319,9 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
         return;
     }
     for (uint32_t o = tid * 4; o < (uint32_t)nwarps * R * blk; o += blockDim.x * 4) sts_u32(hist + o, 0u);
-    double *tsm = reinterpret_cast<double *>(smem + a.extra_off);   // COEF: cos | sin tables ...
-    double *accs = tsm + 2 * nbin;                                   // ... and this CTA's accumulators
-    const int nacc = 2 * a.nharm + 1;
-    if (COEF) {
+    double *tsm = reinterpret_cast<double *>(smem + a.extra_off);   // COEF: cos | sin tables
+    if (COEF)
         for (int i = tid; i < 2 * nbin; i += blockDim.x) tsm[i] = a.tab[i];
-        for (int i = tid; i < nwarps * R * nacc * 32; i += blockDim.x) accs[i] = 0.0;
-    }
 
     // centre constants: slot = 32 centres
     const long long slot0 = ((long long)blockIdx.x * nwarps + warp) * R;
@@ -342,8 +339,12 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
 
     // events of this CTA (a contiguous chunk; rows may be shared with the neighbouring CTAs: drains are atomic)
     const long long n_valid = a.row_start[nprof];
-    const long long ev_lo = min(n_valid, (long long)blockIdx.y * a.ev_per_cta);
-    const long long ev_hi = min(n_valid, ev_lo + a.ev_per_cta);
+    long long ev_lo = min(n_valid, (long long)blockIdx.y * a.ev_per_cta);
+    long long ev_hi = min(n_valid, ev_lo + a.ev_per_cta);
+    if (a.rows_per_cta > 0) {  // whole time slices per CTA: every slice is folded by exactly one CTA
+        const int j_lo = (int)min((long long)nprof, (long long)blockIdx.y * a.rows_per_cta);
+        ev_lo = a.row_start[j_lo], ev_hi = a.row_start[min(nprof, j_lo + a.rows_per_cta)];
+    }
     int j0;  // row of the first event: last j with row_start[j] <= ev_lo
     {
         int lo = 0, hi = nprof;  // invariant: row_start[lo] <= ev_lo, answer in [lo, hi)
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
         j0 = lo;
     }
     const int j1 = nprof;
-    const long long es = ev_lo;  // ev_per_cta is even: 16-byte aligned stream start
+    const long long es = ev_lo & ~1LL;  // 16-byte aligned stream start (a slice boundary may be odd: one event is skipped)
     const int ntiles = ev_hi > es ? (int)((ev_hi - es + TILE_EV - 1) / TILE_EV) : 0;
     const uint32_t bar[2] = {sbase, sbase + 8};
     auto issue = [&](int it) {
@@ -418,9 +419,12 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             }
         }
     };
-    // COEF: fold this thread's columns into its harmonic accumulators (partial DFT of the counts; a DFT is linear, so
-    // the packed counters can be emptied as often as they need) and clear them
-    auto accumulate = [&]() {
+    // COEF: add the harmonic coefficients of this thread's columns (a partial DFT of the counts of time slice `row`: a DFT
+    // is linear, so the packed counters can be emptied as often as they need) to coef[centre][row] and clear the columns.
+    // One thread's successive adds to an address are ordered; with snap_rows no other CTA touches the slice, so the
+    // result is reproducible bit for bit.  Otherwise (slices larger than a CTA's range) the adds of different CTAs
+    // interleave: correct, reproducible to rounding.
+    auto accumulate = [&](int row) {
         const double *tc = tsm, *ts = tsm + nbin;
         const int nh = a.nharm;
 #pragma unroll
@@ -466,31 +470,14 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
                     }
                 }
             }
-            double *ac = accs + (size_t)(warp * R + r) * nacc * 32 + lane;
+            const long long cc = (slot0 + r) * 32 + lane;
+            if (cc < a.n_c && cnt != 0.0) {
+                double *dst = a.coef + ((size_t)cc * nprof + row) * nh * 2;
 #pragma unroll
-            for (int h = 0; h < QL_NHMAX; h++)
-                if (h < nh) ac[(2 * h) * 32] += c[h], ac[(2 * h + 1) * 32] += sn[h];
-            ac[(2 * nh) * 32] += cnt;
-        }
-    };
-    // COEF: the time slice `row` is finished for this CTA: add its coefficients to the global arrays (a slice is
-    // shared with a neighbouring CTA at most at the two ends of this CTA's event range, hence the atomics)
-    auto flush_row = [&](int row) {
-        const int nh = a.nharm;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const long long c = (slot0 + r) * 32 + lane;
-            double *ac = accs + (size_t)(warp * R + r) * nacc * 32 + lane;
-            if (c < a.n_c) {
-                double *dst = a.coef + ((size_t)c * nprof + row) * nh * 2;
-                for (int k = 0; k < 2 * nh; k++) {
-                    const double v = ac[k * 32];
-                    if (v != 0.0) atomicAdd(dst + k, v);
-                }
-                const double n = ac[(2 * nh) * 32];
-                if (n != 0.0) atomicAdd(a.rowcnt + (size_t)c * nprof + row, (unsigned long long)n);
+                for (int h = 0; h < QL_NHMAX; h++)
+                    if (h < nh) atomicAdd(dst + 2 * h, c[h]), atomicAdd(dst + 2 * h + 1, sn[h]);
+                atomicAdd(a.rowcnt + (size_t)cc * nprof + row, (unsigned long long)cnt);
             }
-            for (int k = 0; k < nacc; k++) ac[k * 32] = 0.0;
         }
     };
     auto one = [&](double t) {
@@ -575,7 +562,6 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
     int row = j0;                      // current row
     long long row_end = a.row_start[min(j0 + 1, nprof)];
     int since_drain = 0;
-    bool dirty = false;  // COEF: the accumulators hold part of the current row
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
         mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
@@ -585,11 +571,10 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
         int e = (int)max(0LL, ev_lo - s);  // only the first stage can start before ev_lo
         while (e < cnt) {
             while (s + e >= row_end && row < j1) {  // finished row(s): drain and advance (warp-uniform)
-                if (COEF) {
-                    if (since_drain) accumulate(), since_drain = 0, dirty = true;
-                    if (dirty) flush_row(row), dirty = false;
-                } else if (since_drain) {
-                    drain(row), since_drain = 0;
+                if (since_drain) {
+                    if (COEF) accumulate(row);
+                    else drain(row);
+                    since_drain = 0;
                 }
                 row++;
                 row_end = a.row_start[min(row + 1, nprof)];
@@ -600,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             since_drain += e_end - e;
             e = e_end;
             if (PACKED && since_drain >= a.flush_events) {
-                if (COEF) accumulate(), dirty = true;
+                if (COEF) accumulate(row);
                 else drain(row);
                 since_drain = 0;
             }
@@ -617,11 +602,9 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
             }
         }
     }
-    if (COEF) {
-        if (since_drain) accumulate(), dirty = true;
-        if (dirty) flush_row(min(row, nprof - 1));
-    } else if (since_drain) {
-        drain(min(row, nprof - 1));
+    if (since_drain) {
+        if (COEF) accumulate(min(row, nprof - 1));
+        else drain(min(row, nprof - 1));
     }
 }
 
@@ -1128,20 +1111,19 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         const uint32_t hist_abs = (di.dyn_smem_base + 32 + blk - 1) / blk * blk;
         hist_off = hist_abs - di.dyn_smem_base;
         const uint32_t gap = hist_off - 32;
-        int fit = 0;  // largest stage that fits in the alignment gap in front of the histograms
+        // largest stage that fits in the alignment gap in front of the histograms (fused path: together with the tables)
+        const uint32_t tab_bytes = coef_mode ? 2u * (uint32_t)nbin * 8u : 0u;
+        int fit = 0;
         for (int t = QL_TILE; t >= 256; t -= 64)
-            if (2u * (uint32_t)(t + 16) * 8u <= gap) {
+            if (2u * (uint32_t)(t + 16) * 8u + tab_bytes <= gap) {
                 fit = t;
                 break;
             }
         tile_ev = fit ? fit : QL_TILE;
         const uint32_t tile_region = 2u * (uint32_t)(tile_ev + 16) * 8u;
         tile_off = fit ? 32u : hist_off + hist_bytes;
-        total = std::max(hist_off + hist_bytes, tile_off + tile_region);
-        if (coef_mode) {  // tables + per-thread accumulators behind everything else
-            extra_off = (total + 15u) & ~15u;
-            total = extra_off + (2u * (uint32_t)nbin + (uint32_t)W * R * (2u * nharm + 1u) * 32u) * 8u;
-        }
+        total = std::max(hist_off + hist_bytes, tile_off + tile_region + tab_bytes);
+        extra_off = tile_off + tile_region;  // the tables sit right behind the stages
         if (total <= (uint32_t)di.smem_optin) break;
         if (W > 1) W /= 2;
         else if (R > 1) R /= 2;
@@ -1178,6 +1160,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         a.prof = reinterpret_cast<uint32_t *>(d_lane);
         a.warps = W, a.hist_off = hist_off, a.tile_off = tile_off, a.tile_ev = tile_ev, a.errflag = d_flags + 1;
         a.coef = reinterpret_cast<double *>(d_coef), a.rowcnt = d_rowcnt, a.tab = d_tab, a.nharm = nharm, a.extra_off = extra_off;
+        a.rows_per_cta = 0;
         const int grid_x = (slots + R * W - 1) / (R * W);
         const long long want_y = std::max<long long>(1, 4LL * di.sm_count * ctas_per_sm / grid_x);
         long long per = std::max<long long>((n_ev + want_y - 1) / want_y, 4LL * tile_ev);
@@ -1185,9 +1168,26 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         a.ev_per_cta = per;
         const int grid_y = (int)std::min<long long>(65535, (n_ev + per - 1) / per);
         if ((long long)grid_y * per < n_ev) a.ev_per_cta = ((n_ev + grid_y - 1) / grid_y + 1) & ~1LL;
+        // Fused path with many more time slices than CTAs along y: give every CTA WHOLE slices, so that each slice's
+        // coefficients come from one CTA only (bit-reproducible sums, no contended atomics).  Slices span equal times, so
+        // for a steady source the CTAs stay balanced; k slices per CTA is chosen for well-filled waves.
+        int grid_y_eff = grid_y;
+        if (coef_mode && nprof >= 2 * want_y) {
+            const long long slots = (long long)di.sm_count * ctas_per_sm;
+            int best_k = 0;
+            double best_eff = -1.0;
+            const int k0 = (int)std::max<long long>(1, nprof / want_y);
+            for (int k = std::max(1, k0 - 1); k <= k0 + 2; k++) {
+                const double waves = (double)((nprof + k - 1) / k) * grid_x / (double)slots;
+                const double eff = waves / std::ceil(waves) * (1.0 - 0.04 / std::max(waves, 1.0));
+                if (eff > best_eff) best_eff = eff, best_k = k;
+            }
+            a.rows_per_cta = best_k;
+            grid_y_eff = (nprof + best_k - 1) / best_k;
+        }
         const bool timed = g_qev_ok && g_qev_used < QF_EVPOOL;
         if (timed) HX_CUDA_TRY(cudaEventRecord(g_qev[2 * g_qev_used], st));
-        fn<<<dim3((unsigned)grid_x, (unsigned)grid_y), W * 32, total, st>>>(a);
+        fn<<<dim3((unsigned)grid_x, (unsigned)grid_y_eff), W * 32, total, st>>>(a);
         HX_CHECK_LAUNCH("qffa_lane_kernel");
         if (timed) {
             HX_CUDA_TRY(cudaEventRecord(g_qev[2 * g_qev_used + 1], st));
@@ -1196,6 +1196,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         g_qev_batches++;
         if (n_unsafe > 0) {
             dim3 gf((unsigned)std::min<long long>(n_unsafe, 256), (unsigned)((C + 127) / 128));
+            if (coef_mode) gf.x = 1;  // one thread per centre walks all the (few) photons: its adds are ordered => reproducible
             if (coef_mode) {
                 if (mode == 0) qffa_fix_kernel<0, true><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);
                 else if (mode == 1) qffa_fix_kernel<1, true><<<gf, 128, 0, st>>>(a, d_urange, t_first, delta0, delta1);

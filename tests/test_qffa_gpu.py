@@ -196,3 +196,23 @@ def test_fused_coefficient_drain_equals_the_profile_path(nbin, nprof, n, mode, n
         ref_p = C.qffa_profiles(ts, *cents[k], nbin, nprof)
         assert np.array_equal(prof[k].astype(np.uint64), ref_p)
         np.testing.assert_allclose(fused[k], C.fast_step(ref_p, L, Q, n), rtol=RTOL)
+
+
+def test_fused_drain_with_whole_slices_per_cta_is_bit_reproducible():
+    """The C4 shape in small: 1280 centres (5 CTA columns) and 2048 time slices -- many more slices than CTAs along the
+    event axis, so every CTA folds whole slices and each slice's coefficients are summed by one thread in program order:
+    two runs give the same bits (and the profile path the same numbers to rounding)."""
+    from hendrics_b200.efsearch import _qffa_device_call, _shift_grids, _to_device
+
+    ts = _centred(250_001, 5000.0, seed=77)
+    cents = [(9.85 + 0.00008 * k, 0.0, 0.0) for k in range(1280)]
+    L, Q = _shift_grids(128, 2, 8, True)
+    td = _to_device(ts)
+    a = _qffa_device_call(td, ts[0], ts[-1], cents, 128, 2048, L, Q, 2)
+    b = _qffa_device_call(td, ts[0], ts[-1], cents, 128, 2048, L, Q, 2)
+    assert np.array_equal(a, b)
+    scratch, prof = _qffa_device_call(td, ts[0], ts[-1], cents[:64], 128, 2048, L, Q, 2, want_profiles=True)
+    np.testing.assert_allclose(a[:64], scratch, rtol=1e-12, atol=1e-12 * np.abs(scratch).max())
+    ref_p = C.qffa_profiles(ts, *cents[17], 128, 2048)
+    assert np.array_equal(prof[17].astype(np.uint64), ref_p)
+    np.testing.assert_allclose(a[17], C.fast_step(ref_p, L, Q, 2), rtol=RTOL)
