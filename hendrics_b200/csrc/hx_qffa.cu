@@ -857,9 +857,10 @@ __global__ void __launch_bounds__(256) qffa_step2_kernel(const double *__restric
                                                          const double *__restrict__ Q, int n_lq, int pairs_per_cta,
                                                          const double *__restrict__ base_shift,
                                                          const double *__restrict__ tab, double *__restrict__ stats) {
-    extern __shared__ double ssm[];  // cos | sin | partial sums [groups][pairs][2*NH]
+    extern __shared__ __align__(16) double ssm[];  // (cos, sin) pairs [nbin] | partial sums [groups][pairs][2*NH]
+    double2 *rot = reinterpret_cast<double2 *>(ssm);
     double *part = ssm + 2 * nbin;
-    for (int i = threadIdx.x; i < 2 * nbin; i += blockDim.x) ssm[i] = tab[i];
+    for (int i = threadIdx.x; i < nbin; i += blockDim.x) rot[i] = make_double2(tab[i], tab[nbin + i]);
     __syncthreads();
     const int c = blockIdx.y;
     const int groups = blockDim.x / pairs_per_cta;
@@ -879,13 +880,18 @@ __global__ void __launch_bounds__(256) qffa_step2_kernel(const double *__restric
             int s = (int)r;
             s = p2 ? (s & (nbin - 1)) : ((s % nbin) + nbin) % nbin;  // np.mod -> [0, nbin)
             const double2 *d = reinterpret_cast<const double2 *>(coef + ((size_t)c * nprof + k) * NH * 2);
-            int idx = 0;
+            // the shift is per thread, so this lookup is a random (bank-conflicted) access: ONE 16-byte load for the
+            // first harmonic's rotation; the rotations of harmonics 2..NH follow by angle addition (4 FP64 each)
+            // instead of 2 more conflicted loads each -- the kernel was bound by those loads
+            const double2 w1 = rot[s];
+            double ct = w1.x, st = w1.y;
 #pragma unroll
             for (int h = 0; h < NH; h++) {
-                idx += s;
-                if (p2) idx &= nbin - 1;
-                else idx %= nbin;
-                const double ct = ssm[idx], st = ssm[nbin + idx];
+                if (h > 0) {
+                    const double cn = __fma_rn(ct, w1.x, -__dmul_rn(st, w1.y));
+                    st = __fma_rn(st, w1.x, __dmul_rn(ct, w1.y));
+                    ct = cn;
+                }
                 const double2 v = d[h];  // (Cr, Sr): the same address for every pair of a group: broadcast
                 cs[h] += v.x * ct - v.y * st;
                 sn[h] += v.y * ct + v.x * st;
