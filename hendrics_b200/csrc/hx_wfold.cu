@@ -34,6 +34,7 @@
 // (exactly when the weights are integers and the sums stay below 2^53); statistics within the 1e-9 tolerance.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include <cub/device/device_select.cuh>
 
@@ -43,7 +44,7 @@ namespace hx {
 
 constexpr int WTILE_EV = 512;        // events per pipeline stage
 constexpr int WTILE_PAD = 8;         // events of slack behind a stage (the last register group reads past cnt)
-constexpr uint32_t WSMEM_HDR = 16;   // two mbarriers
+constexpr uint32_t WSMEM_HDR = 32;   // two mbarriers + two "warps done" counters
 
 enum { CELL_F64 = 0, CELL_U32 = 1, CELL_UNIT = 2 };
 enum { WMODE_EDGES = 0, WMODE_FLOOR = 1, WMODE_FAST = 2 };
@@ -162,15 +163,18 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
         if (!tx) mbar_arrive(b);
     };
 
+    int *done = reinterpret_cast<int *>(smem + 16);  // [2] warps that finished the stage
     if (tid == 0) {
         mbar_init(bar[0], 1);
         mbar_init(bar[1], 1);
+        done[0] = 0, done[1] = 0;
         fence_mbar_init();
         fence_proxy_async();
         if (ntiles > 0) issue(0);
         if (ntiles > 1) issue(1);
     }
     __syncthreads();
+    const int nwarps = a.warps;
 
     for (int it = 0; it < ntiles; it++) {
         const int buf = it & 1;
@@ -178,7 +182,9 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
         const int cnt = (int)min((long long)WTILE_EV, e1 - (e0 + (long long)it * WTILE_EV));
         const unsigned char *tp = smem + tile_off + (uint32_t)buf * TILE_T;
         const unsigned char *wp = smem + wt_off + (uint32_t)buf * TILE_W;
-        for (int e = 0; e < cnt; e += U) {
+        // one group of U events; RAGGED: the last, partial group of a stage (events past cnt add zero to a valid cell)
+        auto group = [&](int e, auto ragged_tag) {
+            constexpr bool RAGGED = decltype(ragged_tag)::value;
             double t[U], tt[HAS_FD ? U : 1];
             double w[F64 ? U : 1];
             uint32_t wi[F64 ? 1 : U];
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (e + u >= cnt) {  // ragged end of the last stage: adds zero to a valid cell
+                if (RAGGED && e + u >= cnt) {
                     t[u] = 0.0;
                     if (F64) w[u] = 0.0;
                     else wi[u] = 0u;
@@ -234,11 +240,22 @@ __global__ void __launch_bounds__(512, 1) wfold_kernel(const WFoldArgs a) {
                     }
                 }
             }
-        }
-        __syncthreads();  // every warp is done with stage `buf`
-        if (tid == 0 && it + 2 < ntiles) {
-            fence_proxy_async();
-            issue(it + 2);
+        };
+        int e = 0;
+        for (; e + U <= cnt; e += U) group(e, std::false_type{});  // straight-line main loop: no per-event bounds checks
+        if (e < cnt) group(e, std::true_type{});
+        // stage hand-back without a block barrier (as in K1): the last warp to finish `buf` refills it
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int prev = atomicAdd(&done[buf], 1);
+            if (prev == nwarps - 1) {
+                done[buf] = 0;
+                if (it + 2 < ntiles) {
+                    fence_proxy_async();
+                    issue(it + 2);
+                }
+            }
         }
     }
 
@@ -448,9 +465,10 @@ static wfold_fn_t pick_wfold_M(bool has_fd, int mode) {
 // fp64 cells: (R, U) in {1, 2} x {2, 4}; u32 cells: (1, 4), (2, 2), (4, 2)
 template <int CELL>
 static wfold_fn_t pick_wfold_u32(int R, bool has_fd, int mode) {
+    // events per register group: 8 independent chains per thread (R * U) now that the main loop is straight-line
     return R == 4 ? pick_wfold_M<4, 2, CELL>(has_fd, mode)
-           : R == 2 ? pick_wfold_M<2, 2, CELL>(has_fd, mode)
-                    : pick_wfold_M<1, 4, CELL>(has_fd, mode);
+           : R == 2 ? pick_wfold_M<2, 4, CELL>(has_fd, mode)
+                    : pick_wfold_M<1, 8, CELL>(has_fd, mode);
 }
 static wfold_fn_t pick_wfold(int cell, int R, int U, bool has_fd, int mode) {
     if (cell == CELL_U32) return pick_wfold_u32<CELL_U32>(R, has_fd, mode);
@@ -556,7 +574,8 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
     // work per thread is needed: R trials, and for fp64 cells register groups of U events (U cell loads in flight).
     int R, U;
     if (f64) {
-        R = 2, U = nbin <= 32 ? 2 : 4;
+        // measured on B200 after the straight-line loop (profiles/r02_sweep_wfold.txt): one trial per thread above 32 bins
+        R = nbin <= 32 ? 2 : 1, U = nbin <= 32 ? 2 : 4;
         if (g_wfold_R == 1 || g_wfold_R == 2) R = g_wfold_R;
         if (g_wfold_U == 2 || g_wfold_U == 4) U = g_wfold_U;
     } else {
@@ -588,10 +607,14 @@ int wfold_search_dev_impl(const double *d_times, const double *d_weights, double
         }
     }
     if (g_wfold_W) W = std::min(W, g_wfold_W);
+    // warps per CTA: 1, 2 or a multiple of 4, so that the SM's four schedulers stay evenly loaded (measured on K1 / K2: 3-, 6-
+    // and 11-warp CTAs lose 8-30 %)
+    auto balanced = [](int w) { return w >= 4 ? w / 4 * 4 : w == 3 ? 2 : w; };
+    if (!g_wfold_W) W = balanced(W);
     const long long n_tb = (n_trials + 32LL * R - 1) / (32LL * R);
-    {  // few trials: smaller CTAs so that every SM gets one
+    {  // very few trials: smaller CTAs so that every SM gets one (the event splitting below multiplies the CTAs otherwise)
         const long long want = (n_tb + di.sm_count - 1) / di.sm_count;
-        if (want < W) W = (int)std::max<long long>(1, want);
+        if (want < W && want <= 2) W = (int)std::max<long long>(1, want);
     }
     const uint32_t smem_bytes = fixed + (uint32_t)W * R * blk;
     const int ctas_per_sm = std::max(1, di.smem_per_sm / (int)(smem_bytes + di.reserved_smem));
