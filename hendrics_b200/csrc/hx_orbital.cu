@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) orbital_fold_kernel(const OrbArgs a) {
         mbar_wait(bar[buf], (uint32_t)(it >> 1) & 1u);
         const int cnt = (int)min((long long)OTILE_EV, e1 - (e0 + (long long)it * OTILE_EV));
         const double *tp = reinterpret_cast<const double *>(smem + tile_off + (uint32_t)buf * TILE_BYTES);
-#pragma unroll 2
+#pragma unroll 4
         for (int e = 0; e < cnt; e++) {
             const double u = __dsub_rn(demodulate(tp[e], T0, a.X, a.Porb), u0);
             // the fast branch of the search on `u`: phase = u*f + ((0.5*u)*u)*fd, minus its floor, times nbin, floored
@@ -169,7 +169,19 @@ int orbital_search_dev_impl(const double *d_times, int64_t n_ev, double freq, do
         return HX_ERR_ARG;
     }
     const long long n_tb = (n_t0 + 31) / 32;
-    W = (int)std::max<long long>(1, std::min<long long>(W, (n_tb + di.sm_count - 1) / di.sm_count));
+    // Warps per CTA: the kernel is a long dependent chain per event (two sin(), two divisions), so it lives on resident
+    // warps.  The stage buffers are per CTA: larger CTAs leave room for more warps per SM (W = 1: 12 warps per SM at
+    // nbin = 64, W = 8: 24), and the event splitting below provides the CTAs when there are few T0 blocks (measured:
+    // 1e6 events x 4736 T0, 42.5 -> see profiles/r02_orbital_throughput.txt).  1, 2 or a multiple of 4 warps.
+    {
+        int best_w = 1, best_res = 0;
+        for (int w : {1, 2, 4, 8}) {
+            if (w > W || w > n_tb) continue;
+            const int k = std::min(16, di.smem_per_sm / (int)(fixed + (uint32_t)w * blk + di.reserved_smem));
+            if (k * w > best_res) best_res = k * w, best_w = w;
+        }
+        W = best_w;
+    }
     const long long grid_x = (n_tb + W - 1) / W;
     const uint32_t smem_bytes = fixed + (uint32_t)W * blk;
     const int ctas_per_sm = std::max(1, std::min(16, di.smem_per_sm / (int)(smem_bytes + di.reserved_smem)));
