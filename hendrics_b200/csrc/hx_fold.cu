@@ -48,6 +48,9 @@ namespace hx {
 #ifndef HX_FOLD_HYB
 #define HX_FOLD_HYB 0  // M2T experiment: of every group of UE events, the fdot term of the last HX_FOLD_HYB is recomputed per thread
 #endif                 // (2 FP64 ops per event and thread) instead of loaded from the tile (one broadcast wavefront per event and warp)
+#ifndef HX_FOLD_UE_FD
+#define HX_FOLD_UE_FD 8  // events per register group of the plain (f, fdot) loop with <= 2 trials per thread (4 and 16 measured: see DESIGN)
+#endif
 #ifndef HX_FOLD_SKEW_UE2
 #define HX_FOLD_SKEW_UE2 4  // events per register group of the skewed (f, fdot) loop with 2 trials per thread
 #endif
@@ -212,7 +215,7 @@ struct EvGroup {
 // (R*UE) to cover the FP64 latency with the few warps the histograms leave room for
 template <int R, bool HAS_FD, bool SKEW>
 struct GroupSize {
-    static constexpr int value = HAS_FD ? (SKEW ? (R >= 4 ? 2 : R >= 2 ? HX_FOLD_SKEW_UE2 : 8) : (R >= 8 ? 2 : R >= 4 ? 4 : 8))
+    static constexpr int value = HAS_FD ? (SKEW ? (R >= 4 ? 2 : R >= 2 ? HX_FOLD_SKEW_UE2 : 8) : (R >= 8 ? 2 : R >= 4 ? 4 : HX_FOLD_UE_FD))
                                         : (R >= 4 ? 2 : 4);
 };
 
@@ -231,7 +234,9 @@ __global__ void __launch_bounds__(512, 1) fold_kernel(const FoldArgs a) {
     constexpr bool EXACT = MODE == MODE_EXACT;
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr bool SKEW = !EXACT && (!HAS_FD || HX_FOLD_SKEW_FD);  // the exact-phase extension keeps the plain loop
-    constexpr int UE = GroupSize<R, HAS_FD, SKEW>::value;
+    // plain (f, fdot) loop with <= 2 trials per thread: 8 events per register group with packed counters (nbin >= 128), 4 with
+    // plain ones (measured on B200, profiles/r02_variants_ue.txt: nbin 64 +4.5 %, nbin 32 +2.5 %, nbin 128 -4 % with 4)
+    constexpr int UE = (HAS_FD && !SKEW && R <= 2 && !PACKED && !EXACT) ? 4 : GroupSize<R, HAS_FD, SKEW>::value;
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t blk = (uint32_t)a.nbin << (PACKED ? 6 : 7);  // bytes of one (warp, r) histogram block
