@@ -205,6 +205,7 @@ def test_fused_drain_with_whole_slices_per_cta_is_bit_reproducible():
     from hendrics_b200.efsearch import _qffa_device_call, _shift_grids, _to_device
 
     ts = _centred(250_001, 5000.0, seed=77)
+    ts = ts[~((ts > 300.0) & (ts < 900.0))]  # a data gap: ~250 empty time slices in a row, CTAs with nothing to fold
     cents = [(9.85 + 0.00008 * k, 0.0, 0.0) for k in range(1280)]
     L, Q = _shift_grids(128, 2, 8, True)
     td = _to_device(ts)
