@@ -139,6 +139,12 @@ int hx_wfold_last_kernel_ms(double *ms, int *cell_kind, int64_t *n_events_folded
  *   L, Q      [n_lq]  bin-shift pairs (the meshgrid of efsearch.py:921, flattened row-major)
  *   stats     [n_centres * n_lq]
  *   profiles  [n_centres * nprof * nbin] uint32 2-D profiles (time slice, phase bin), or NULL
+ *
+ * With profiles == NULL and nharm <= 4 (sorted times, power-of-two nbin) the 2-D profiles never leave the SM:
+ * every finished time slice is reduced to its 2 * nharm harmonic coefficients there (the only thing _fast_step
+ * needs of it), so the call needs 8 * nprof * (2 * nharm + 1) bytes of scratch per centre instead of
+ * 4 * nprof * nbin.  Statistics are the same to fp64 summation order (1e-12); with profiles != NULL the
+ * counts are materialised and bit-exact.
  */
 int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, const double *mean_fd,
                    const double *mean_fdd, int64_t n_centres, int nbin, int nprof, const double *L, const double *Q,
