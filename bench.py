@@ -310,10 +310,15 @@ def run_c4(args):
     # e2e: host array in (H2D of the 0.8 GB event list every step), host stats out
     pin = torch.from_numpy(tc).pin_memory()
     pin_np = pin.numpy()
+    from hendrics_b200.fastfold import _qffa_host_call
+
     def step_e2e():
-        # what search_with_qffa does: N ranks upload 1/N of the (replicated) list each + one NVLink all-gather
-        d = hdist.upload_replicated(pin_np)
-        return _qffa_device_call(d, tc[0], tc[-1], cents, nbin, nprof, L, Q, n)
+        # what search_with_qffa does.  N ranks: each uploads 1/N of the (replicated) list + one NVLink all-gather, then
+        # the device entry; one GPU: the host entry, which streams the list up while K2 folds the chunks already there
+        if world > 1:
+            d = hdist.upload_replicated(pin_np)
+            return _qffa_device_call(d, tc[0], tc[-1], cents, nbin, nprof, L, Q, n)
+        return _qffa_host_call(pin_np, cents, nbin, nprof, L, Q, n)
     step_e2e()
     barrier()
     t0 = time.perf_counter()

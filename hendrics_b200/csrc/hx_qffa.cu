@@ -298,6 +298,11 @@ struct QLaneArgs {
     int nharm;                    // <= QL_NHMAX
     uint32_t extra_off;           // the staged tables
     int rows_per_cta;             // > 0: CTA y folds the time slices [y * rows_per_cta, (y + 1) * rows_per_cta) and nothing else
+    // streamed upload (hx_qffa_search from a host array): the events arrive chunk by chunk over PCIe WHILE this kernel
+    // runs; *progress = number of chunks of `chunk_events` events already in place (written by the copy stream after
+    // each chunk).  A CTA waits until its whole event range has arrived.  NULL: everything is resident.
+    const int *progress;
+    long long chunk_events;
 };
 constexpr int QL_NHMAX = 4;
 
@@ -344,6 +349,27 @@ __global__ void __launch_bounds__(512, 1) qffa_lane_kernel(const QLaneArgs a) {
     if (a.rows_per_cta > 0) {  // whole time slices per CTA: every slice is folded by exactly one CTA
         const int j_lo = (int)min((long long)nprof, (long long)blockIdx.y * a.rows_per_cta);
         ev_lo = a.row_start[j_lo], ev_hi = a.row_start[min(nprof, j_lo + a.rows_per_cta)];
+    }
+    if (a.progress != nullptr && ev_hi > ev_lo) {
+        if (tid == 0) {
+            const int need = (int)((ev_hi + a.chunk_events - 1) / a.chunk_events);
+            const volatile int *prog = a.progress;
+            unsigned long long t0 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*prog < need) {
+                __nanosleep(2000);
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {  // 20 s without the chunk: the host side failed; give up loudly
+                    atomicExch(a.errflag, 2);
+                    break;
+                }
+            }
+            __threadfence();
+            fence_proxy_async();  // the copy engine's writes, seen by this thread, before the bulk copies that read them
+        }
+        __syncthreads();
+        if (*reinterpret_cast<volatile int *>(a.errflag) == 2) return;
     }
     int j0;  // row of the first event: last j with row_start[j] <= ev_lo
     {
@@ -678,6 +704,7 @@ __global__ void qffa_prepass_kernel(const double *__restrict__ t, long long n, d
         if (!(v >= t_first) || (i + 1 < n && t[i + 1] < v)) bad = true;
     }
     if (bad) atomicExch(flag, 1);
+    if (row_start == nullptr) return;  // sortedness only (the boundaries came from the host: streamed upload)
     if (gid <= nprof) {
         const int j = (int)gid;  // smallest e with row(t[e]) >= j; row nprof = "dropped"
         long long lo = 0, hi = n;
@@ -1018,7 +1045,11 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
                           const double *mean_f, const double *mean_fd, const double *mean_fdd, int64_t n_centres,
                           int nbin, int nprof, double delta0, double delta1, const double *d_L, const double *d_Q,
                           int64_t n_lq, const double *d_base, const double *d_tab, int nharm, double *d_stats,
-                          uint32_t *d_profiles, cudaStream_t st, int transient_levels, int transient_rows) {
+                          uint32_t *d_profiles, cudaStream_t st, int transient_levels, int transient_rows,
+                          const double *h_t = nullptr, bool *uploaded = nullptr) {
+    // h_t != NULL: the events are still in HOST memory (hx_qffa_search); d_t is an empty device buffer that this function
+    // fills -- streamed in chunks WHILE K2 folds the chunks that have arrived, when the fused path applies -- and
+    // *uploaded tells the caller whether that happened (a `return 1` before it leaves the upload to the caller).
     const bool p2 = (nbin & (nbin - 1)) == 0;
     if (!g_qffa_lane || !g_qffa_fast || !p2 || nbin < 8 || nbin > 512 || n_centres < 1) return 1;
     int mode = 0;
@@ -1048,23 +1079,116 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
             if (p) cudaFreeAsync(p, s);
         }
     } f1{d_misc, st}, f2{d_cent, st}, f3{d_lane, st}, f4{d_plain, st}, f5{d_coef, st};
-    const size_t misc_bytes = (size_t)(nprof + 1 + 2) * 8 + 16;
+    const size_t misc_bytes = (size_t)(nprof + 1 + 2) * 8 + 16;  // row_start | urange | flags[2] | upload progress
     HX_CUDA_TRY(cudaMallocAsync(&d_misc, misc_bytes, st));
     HX_CUDA_TRY(cudaMemsetAsync(d_misc, 0, misc_bytes, st));
     long long *d_rowstart = reinterpret_cast<long long *>(d_misc), *d_urange = d_rowstart + nprof + 1;
     int *d_flags = reinterpret_cast<int *>(d_urange + 2);  // [0] unsorted, [1] layout error
-    {
+    // streamed upload: fused single-batch searches on large event lists
+    bool streamed = false;
+    if (h_t) {
+        bool ok = d_profiles == nullptr && nharm >= 1 && nharm <= QL_NHMAX && n_ev >= (1 << 22) &&
+                  (size_t)n_centres * nprof * (2 * nharm + 1) * 8 <= ((size_t)2048 << 20);
+        if (const char *e = getenv("HX_QFFA_FUSE")) ok = ok && atoi(e) != 0;
+        if (const char *e = getenv("HX_QFFA_STREAM")) ok = ok && atoi(e) != 0;  // A-B hook
+        streamed = ok;
+        if (!streamed) {  // plain upload, then everything as for resident events
+            HX_CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d_t), h_t, (size_t)n_ev * 8, cudaMemcpyHostToDevice, st));
+            if (uploaded) *uploaded = true;
+        }
+    }
+    cudaStream_t cs = nullptr;  // copy stream of the streamed upload
+    cudaEvent_t ev_sync = nullptr;
+    struct StreamGuard {
+        cudaStream_t &s;
+        cudaEvent_t &e;
+        ~StreamGuard() {
+            if (s) cudaStreamSynchronize(s);  // no copy into the caller's buffer may outlive this call
+            if (e) cudaEventDestroy(e);
+            if (s) cudaStreamDestroy(s);
+        }
+    } stream_guard{cs, ev_sync};
+    long long chunk_events = 0;
+    int n_chunks = 0;
+    std::vector<int> h_prog;
+    int *d_prog = nullptr;
+    bool copies_issued = false;
+    auto issue_copies = [&]() -> int {  // chunk c, then "c + 1 chunks are in place", on the copy stream
+        for (int c = 0; c < n_chunks; c++) {
+            const long long off = (long long)c * chunk_events, cnt = std::min<long long>(chunk_events, n_ev - off);
+            HX_CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d_t) + off, h_t + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, cs));
+            HX_CUDA_TRY(cudaMemcpyAsync(d_prog, &h_prog[c], sizeof(int), cudaMemcpyHostToDevice, cs));
+        }
+        HX_CUDA_TRY(cudaEventRecord(ev_sync, cs));
+        copies_issued = true;
+        return HX_OK;
+    };
+    bool pinned = false;
+    int h_flags[2] = {0, 0};
+    long long h_urange[2] = {0, 0};
+    if (!streamed) {
         const long long want = std::max<long long>((n_ev + 255) / 256, (nprof + 3 + 255) / 256);
         qffa_prepass_kernel<<<(unsigned)std::min<long long>(std::max<long long>(want, 1), 2368), 256, 0, st>>>(
             d_t, n_ev, t_first, delta1, nprof, t_safe, d_rowstart, d_urange, d_flags);
         HX_CHECK_LAUNCH("qffa_prepass_kernel");
+        HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
+        HX_CUDA_TRY(cudaMemcpyAsync(h_urange, d_urange, 16, cudaMemcpyDeviceToHost, st));
+        HX_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_flags[0]) return 1;  // unsorted input: the lane = event kernel copes with it
+    } else {
+        if (uploaded) *uploaded = true;
+        HX_CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        HX_CUDA_TRY(cudaEventCreateWithFlags(&ev_sync, cudaEventDisableTiming));
+        n_chunks = (int)std::min<long long>(16, std::max<long long>(2, n_ev / (1 << 22)));  // >= 32 MB per chunk
+        chunk_events = ((n_ev + n_chunks - 1) / n_chunks + 1) & ~1LL;
+        n_chunks = (int)((n_ev + chunk_events - 1) / chunk_events);
+        h_prog.resize(n_chunks);
+        for (int c = 0; c < n_chunks; c++) h_prog[c] = c + 1;
+        d_prog = d_flags + 2;  // zeroed by the memset of d_misc above
+        // the copies may only start once that memset has run
+        HX_CUDA_TRY(cudaEventRecord(ev_sync, st));
+        HX_CUDA_TRY(cudaStreamWaitEvent(cs, ev_sync, 0));
+        cudaPointerAttributes pa{};
+        pinned = cudaPointerGetAttributes(&pa, h_t) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();  // an unregistered host pointer is not an error here
+        // page-locked source: the copies are asynchronous, start them now and search the slice boundaries meanwhile;
+        // pageable source: cudaMemcpyAsync blocks the host, so K2 is launched first (below) and then fed
+        if (pinned) {
+            int rcc = issue_copies();
+            if (rcc) return rcc;
+        }
+        // slice boundaries and the |t| < t_safe range by binary search on the HOST array, with the kernels' arithmetic
+        // (assumes sorted times; sortedness is verified on the device once everything is up, see below)
+        std::vector<long long> rs((size_t)nprof + 3);
+        auto before_row = [&](long long e, int j) {
+            const double jf = (h_t[e] - t_first) * delta1;
+            return j == nprof ? jf < (double)nprof : jf < (double)j;
+        };
+        long long prev = 0;
+        for (int j = 0; j <= nprof; j++) {  // galloping from the previous boundary: the probes stay local
+            long long lo = prev, hi = n_ev, stepg = 1024;
+            while (lo + stepg < n_ev && before_row(lo + stepg, j)) lo += stepg, stepg *= 2;
+            hi = std::min<long long>(n_ev, lo + stepg);
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (before_row(mid, j)) lo = mid + 1;
+                else hi = mid;
+            }
+            rs[j] = prev = lo;
+        }
+        for (int k = 0; k < 2; k++) {  // u0: first t > -t_safe ; u1: first t >= t_safe
+            long long lo = 0, hi = n_ev;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                const bool before = k == 0 ? (h_t[mid] <= -t_safe) : (h_t[mid] < t_safe);
+                if (before) lo = mid + 1;
+                else hi = mid;
+            }
+            rs[(size_t)nprof + 1 + k] = h_urange[k] = lo;
+        }
+        HX_CUDA_TRY(cudaMemcpyAsync(d_rowstart, rs.data(), rs.size() * 8, cudaMemcpyHostToDevice, st));
+        HX_CUDA_TRY(cudaStreamSynchronize(st));  // rs is a local: the copy must have read it before it goes away
     }
-    int h_flags[2] = {0, 0};
-    long long h_urange[2] = {0, 0};
-    HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
-    HX_CUDA_TRY(cudaMemcpyAsync(h_urange, d_urange, 16, cudaMemcpyDeviceToHost, st));
-    HX_CUDA_TRY(cudaStreamSynchronize(st));
-    if (h_flags[0]) return 1;  // unsorted input: the lane = event kernel copes with it
     const long long n_unsafe = std::max<long long>(0, h_urange[1] - h_urange[0]);
 
     std::vector<double> hc(3 * (size_t)n_centres);
@@ -1167,6 +1291,7 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
         a.warps = W, a.hist_off = hist_off, a.tile_off = tile_off, a.tile_ev = tile_ev, a.errflag = d_flags + 1;
         a.coef = reinterpret_cast<double *>(d_coef), a.rowcnt = d_rowcnt, a.tab = d_tab, a.nharm = nharm, a.extra_off = extra_off;
         a.rows_per_cta = 0;
+        a.progress = streamed ? d_prog : nullptr, a.chunk_events = chunk_events;
         const int grid_x = (slots + R * W - 1) / (R * W);
         const long long want_y = std::max<long long>(1, 4LL * di.sm_count * ctas_per_sm / grid_x);
         long long per = std::max<long long>((n_ev + want_y - 1) / want_y, 4LL * tile_ev);
@@ -1200,6 +1325,18 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
             g_qev_used++;
         }
         g_qev_batches++;
+        if (streamed) {
+            if (!copies_issued) {  // pageable source: the kernel is already waiting for its chunks; feed it
+                int rcc = issue_copies();
+                if (rcc) return rcc;
+            }
+            // everything is up once the copy stream gets here: verify, on the device, the sortedness the host-side
+            // boundaries relied on (the result is discarded and the caller falls back if it does not hold)
+            HX_CUDA_TRY(cudaStreamWaitEvent(st, ev_sync, 0));
+            qffa_prepass_kernel<<<(unsigned)std::min<long long>(std::max<long long>((n_ev + 255) / 256, 1), 2368), 256, 0, st>>>(
+                d_t, n_ev, t_first, delta1, nprof, t_safe, nullptr, nullptr, d_flags);
+            HX_CHECK_LAUNCH("qffa_prepass_kernel");
+        }
         if (n_unsafe > 0) {
             dim3 gf((unsigned)std::min<long long>(n_unsafe, 256), (unsigned)((C + 127) / 128));
             if (coef_mode) gf.x = 1;  // one thread per centre walks all the (few) photons: its adds are ordered => reproducible
@@ -1258,10 +1395,15 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
     }
     HX_CUDA_TRY(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
     HX_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_flags[1] == 2) {
+        set_error("qffa_lane_kernel: the streamed upload of the events stalled");
+        return HX_ERR_CUDA;
+    }
     if (h_flags[1]) {
         set_error("qffa_lane_kernel: shared-memory layout mismatch");
         return HX_ERR_INTERNAL;
     }
+    if (streamed && h_flags[0]) return 1;  // unsorted after all: the events are resident now, the caller falls back
     if (g_qev_used > 0) {
         double sum = 0.0;
         for (int i = 0; i < g_qev_used; i++) {
@@ -1278,7 +1420,8 @@ static int qffa_lane_path(const DeviceInfo &di, const double *d_t, int64_t n_ev,
 int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double t_last, const double *mean_f,
                          const double *mean_fd, const double *mean_fdd, int64_t n_centres, int nbin, int nprof,
                          const double *L, const double *Q, int64_t n_lq, int nharm, double *d_stats,
-                         uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0, int transient_rows = 0) {
+                         uint32_t *d_profiles, cudaStream_t st, int transient_levels = 0, int transient_rows = 0,
+                         const double *h_t = nullptr) {
     std::lock_guard<std::recursive_mutex> api_lock(api_mutex());
     if (!d_t || !mean_f || !mean_fd || !mean_fdd || !L || !Q || !d_stats) {
         set_error("hx_qffa_search: null pointer argument");
@@ -1346,10 +1489,13 @@ int qffa_search_dev_impl(const double *d_t, int64_t n_ev, double t_first, double
     }
     {
         // preferred path: lane = centre (conflict-free atomics); falls through when not eligible
+        bool uploaded = false;
         int rl = qffa_lane_path(di, d_t, n_ev, t_first, t_last, mean_f, mean_fd, mean_fdd, n_centres, nbin, nprof,
                                 delta0, delta1, d_L, d_Q, n_lq, d_base, d_tab, nharm, d_stats, d_profiles, st,
-                                transient_levels, transient_rows);
+                                transient_levels, transient_rows, h_t, &uploaded);
         if (rl <= 0) return rl;
+        if (h_t && !uploaded)  // the lane = centre path declined before touching the events: plain upload for the fallback
+            HX_CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d_t), h_t, (size_t)n_ev * 8, cudaMemcpyHostToDevice, st));
     }
     const size_t prof_elems = (size_t)nprof * nbin;
     if (!d_profiles) HX_CUDA_TRY(cudaMallocAsync(&d_scratch, prof_elems * cmax * sizeof(uint32_t), st));
@@ -1548,15 +1694,16 @@ int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, co
     }
     hx::DeviceGuard dev_guard;  // declared before the device buffers: they are freed before the device is restored
     HX_CUDA_TRY(dev_guard.enter(device));
-    hx::DevBuf dt, ds, dp;
+    // the events are uploaded by the search itself: in chunks, while K2 already folds the chunks that have arrived
+    // (fused path, large lists), else in one copy
+    hx::AsyncBuf dt(0), ds(0), dp(0);
     HX_CUDA_TRY(dt.alloc((size_t)n_ev * 8));
     HX_CUDA_TRY(ds.alloc((size_t)n_centres * n_lq * 8));
     const size_t pe = (size_t)n_centres * nprof * nbin;
     if (profiles) HX_CUDA_TRY(dp.alloc(pe * 4));
-    HX_CUDA_TRY(cudaMemcpy(dt.p, times_c, (size_t)n_ev * 8, cudaMemcpyHostToDevice));
     int rc = hx::qffa_search_dev_impl(dt.as<double>(), n_ev, times_c[0], times_c[n_ev - 1], mean_f, mean_fd, mean_fdd,
                                       n_centres, nbin, nprof, L, Q, n_lq, nharm, ds.as<double>(),
-                                      profiles ? dp.as<uint32_t>() : nullptr, 0);
+                                      profiles ? dp.as<uint32_t>() : nullptr, 0, 0, 0, times_c);
     if (rc) return rc;
     HX_CUDA_TRY(cudaMemcpy(stats, ds.p, (size_t)n_centres * n_lq * 8, cudaMemcpyDeviceToHost));
     if (profiles) HX_CUDA_TRY(cudaMemcpy(profiles, dp.p, pe * 4, cudaMemcpyDeviceToHost));

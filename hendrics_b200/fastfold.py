@@ -146,6 +146,28 @@ def _qffa_device_call(times_d, t_first, t_last, centres, nbin, nprof, L, Q, n, w
     return stats
 
 
+def _qffa_host_call(times, centres, nbin, nprof, L, Q, n):
+    """``hx_qffa_search`` straight from the HOST event array: the library uploads it itself -- in chunks, while K2 already
+    folds the chunks that have arrived (fused path, large lists) -- so a single-GPU search of 1e8 events does not wait
+    for its 0.8 GB copy first.  Statistics (n_centres,) + L.shape."""
+    import torch
+
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    cents = np.ascontiguousarray(np.asarray(centres, dtype=np.float64).reshape(-1, 3))
+    mf, mfd, mfdd = (np.ascontiguousarray(cents[:, i]) for i in range(3))
+    Lf, Qf = _cabi.as_f64(L.ravel()), _cabi.as_f64(Q.ravel())
+    stats = np.empty((cents.shape[0], Lf.size), dtype=np.float64)
+    from .search import _device
+
+    dev = _device(None)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().hx_qffa_search(
+            _cabi.dptr(times), times.size, _cabi.dptr(mf), _cabi.dptr(mfd), _cabi.dptr(mfdd), cents.shape[0], int(nbin),
+            int(nprof), _cabi.dptr(Lf), _cabi.dptr(Qf), Lf.size, int(n), _cabi.dptr(stats), None, dev.index or 0)
+    _cabi.check(rc)
+    return stats.reshape((cents.shape[0],) + L.shape)
+
+
 def _to_device(times, device=None):
     import torch
 
@@ -195,11 +217,16 @@ def search_with_qffa(times, f0, f1, fdot=0, fddot=0, nbin=16, nprof=None, npfact
     centres, _ = qffa_centres(f0, f1, ev.length, npfact, fdot, fddot)
     plane = ShiftPlane(nbin, npfact, oversample, search_fdot)
     to_f, to_fdot = plane.scale(ev.first, ev.last)
-    times_d = ev.on_device()
+    if dist.is_distributed():  # replicated list: 1/N per rank over PCIe + one NVLink all-gather, then the device entry
+        times_d = ev.on_device()
 
-    stats = dist.sharded_rows(
-        lambda rows: _qffa_device_call(times_d, ev.first, ev.last, rows, nbin, nprof, plane.L, plane.Q, n),
-        np.asarray(centres, dtype=np.float64))  # (n_centres, nL, nQ)
+        def fold(rows):
+            return _qffa_device_call(times_d, ev.first, ev.last, rows, nbin, nprof, plane.L, plane.Q, n)
+    else:  # one GPU: the host entry streams the events up while K2 folds what has arrived
+        def fold(rows):
+            return _qffa_host_call(ev.times, rows, nbin, nprof, plane.L, plane.Q, n)
+
+    stats = dist.sharded_rows(fold, np.asarray(centres, dtype=np.float64))  # (n_centres, nL, nQ)
 
     nL, nQ = plane.L.shape
     shape = (nL * len(centres), nQ)

@@ -217,3 +217,35 @@ def test_fused_drain_with_whole_slices_per_cta_is_bit_reproducible():
     ref_p = C.qffa_profiles(ts, *cents[17], 128, 2048)
     assert np.array_equal(prof[17].astype(np.uint64), ref_p)
     np.testing.assert_allclose(a[17], C.fast_step(ref_p, L, Q, 2), rtol=RTOL)
+
+
+def test_streamed_upload_from_host_memory(monkeypatch):
+    """hx_qffa_search on a host array of >= 2^22 events uploads it in chunks while K2 already folds the chunks that have
+    arrived (the kernel waits on a progress word written by the copy stream).  Same bits as the plain upload, from
+    pageable and from page-locked memory (the two issue orders), and an unsorted list -- detected on the device only after
+    the optimistic run -- still gives the right answer through the fallback."""
+    import torch
+
+    from hendrics_b200.efsearch import _shift_grids
+    from hendrics_b200.fastfold import _qffa_host_call
+
+    rng = np.random.default_rng(5)
+    ts = np.sort(rng.uniform(-2500.0, 2500.0, 4_500_001))
+    cents = [(9.85 + 0.0001 * k, 0.0, 0.0) for k in range(96)]
+    L, Q = _shift_grids(64, 2, 4, True)
+    monkeypatch.setenv("HX_QFFA_STREAM", "0")
+    plain = _qffa_host_call(ts, cents, 64, 1024, L, Q, 2)
+    monkeypatch.setenv("HX_QFFA_STREAM", "1")
+    pageable = _qffa_host_call(ts, cents, 64, 1024, L, Q, 2)
+    pinned = torch.from_numpy(ts).pin_memory().numpy()
+    locked = _qffa_host_call(pinned, cents, 64, 1024, L, Q, 2)
+    np.testing.assert_allclose(pageable, plain, rtol=1e-13, atol=1e-13 * np.abs(plain).max())
+    np.testing.assert_allclose(locked, plain, rtol=1e-13, atol=1e-13 * np.abs(plain).max())
+    ref_p = C.qffa_profiles(ts, *cents[40], 64, 1024)
+    np.testing.assert_allclose(pageable[40], C.fast_step(ref_p, L, Q, 2), rtol=RTOL)
+    # unsorted: two distant blocks swapped
+    bad = ts.copy()
+    bad[1000:2000], bad[3_000_000:3_001_000] = ts[3_000_000:3_001_000].copy(), ts[1000:2000].copy()
+    got = _qffa_host_call(bad, cents[:8], 64, 1024, L, Q, 2)
+    ref_b = C.qffa_profiles(bad, *cents[3], 64, 1024)
+    np.testing.assert_allclose(got[3], C.fast_step(ref_b, L, Q, 2), rtol=RTOL)
