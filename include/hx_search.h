@@ -145,6 +145,10 @@ int hx_wfold_last_kernel_ms(double *ms, int *cell_kind, int64_t *n_events_folded
  * needs of it), so the call needs 8 * nprof * (2 * nharm + 1) bytes of scratch per centre instead of
  * 4 * nprof * nbin.  Statistics are the same to fp64 summation order (1e-12); with profiles != NULL the
  * counts are materialised and bit-exact.
+ * hx_qffa_search (host array in) uploads the events itself; on that fused path and for >= 2^22 events it does
+ * so in chunks on a copy stream WHILE the kernel folds the chunks already in place (page-locked `times_c` gives
+ * the best overlap; pageable works).  The times must be sorted for this (verified on the device; unsorted
+ * input is still handled, by the slower lane = event kernel).
  */
 int hx_qffa_search(const double *times_c, int64_t n_ev, const double *mean_f, const double *mean_fd,
                    const double *mean_fdd, int64_t n_centres, int nbin, int nprof, const double *L, const double *Q,
