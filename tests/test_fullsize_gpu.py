@@ -44,6 +44,18 @@ def test_c2_full_grid_subset_against_oracle():
     assert np.array_equal(p_a + p_b, p_sub[:, :200])
     # the pulsation injected at 1/0.101 Hz is the global maximum of the 10^6-trial periodogram
     assert abs(f[np.argmax(stats)] - 1 / 0.101) < 2e-5
+    # ALL 10^6 trials: the profiles of the whole grid (scratch variant), bit-exact against the oracle on the subset,
+    # every one of them holding every selected event exactly once, and the chi^2 recomputed from them on the host equal
+    # to the statistics of the fused-epilogue run above -- so every statistic of the grid is tied to integer counts
+    s_all, p_all = fold_profiles(t, freqs, [0.0], nbin=16, nharm=0)
+    p_all = p_all[0]
+    _, ref_p = C.fold_search(t, freqs[pick], [0.0], 16, 0, want_profiles=True)
+    assert np.array_equal(p_all[pick], ref_p[0])
+    assert np.all(p_all.sum(axis=1) == t.size)
+    mean = t.size / 16.0
+    chi2 = ((p_all - mean) ** 2 / mean).sum(axis=1)
+    np.testing.assert_allclose(stats, chi2, rtol=1e-12)
+    np.testing.assert_allclose(s_all[0], stats, rtol=1e-13)
 
 
 def test_c3_slice_full_event_count_against_oracle():
