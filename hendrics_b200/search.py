@@ -103,6 +103,21 @@ def fold_windows_device(ts_d, win_start, win_stop, mode, freqs_d, fdots_d, nbin,
     return stats, status, total
 
 
+def _segment_slices(times_d, start_times, segment_size, half_open):
+    """``[(lo, hi, t[lo], t[hi - 1]), ...]``: the events with ``s <= t < s + segment_size`` (``<=`` when not half-open) of
+    every segment start ``s`` as index ranges of the SORTED device array; None when the array is not sorted."""
+    torch = _torch()
+    if not _is_sorted_device(times_d):
+        return None
+    starts = torch.as_tensor(np.asarray(start_times, dtype=np.float64), device=times_d.device)
+    lo = torch.searchsorted(times_d, starts, right=False)
+    hi = torch.searchsorted(times_d, starts + float(segment_size), right=not half_open)
+    n = times_d.numel()
+    edges = torch.stack([times_d[lo.clamp(max=n - 1)], times_d[(hi - 1).clamp(min=0)]])
+    lo, hi, edges = lo.cpu().numpy(), hi.cpu().numpy(), edges.cpu().numpy()
+    return [(int(a), int(b), float(x), float(y)) for a, b, x, y in zip(lo, hi, edges[0], edges[1])]
+
+
 def _is_sorted_device(t_d):
     return t_d.numel() < 2 or bool((t_d[1:] >= t_d[:-1]).all().item())
 
@@ -205,16 +220,24 @@ def _folding_search(
         _, status, total = fold_windows_device(times_d, start_times, start_times + segment_size, WIN_SEGMENTS, freqs_d,
                                                fdots_d, nbin, nharm, origin=0.0, segment_size=segment_size, want_sum=True)
         return _grids_and_stats(frequencies, fdots, total, int(np.count_nonzero(status == 1)), device_stats=_device_stats)
-    for s in start_times:
-        if UPSTREAM_SEMANTICS["drop_last_event"]:
-            good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open
+    # Sorted times (the usual case): a segment is a SLICE of the device array -- its bounds come from one searchsorted
+    # for all segments and one small D2H copy -- instead of a boolean mask + compaction over the whole list per segment.
+    ranges = _segment_slices(times_d, start_times, segment_size, UPSTREAM_SEMANTICS["drop_last_event"])
+    for k, s in enumerate(start_times):
+        if ranges is not None:
+            lo, hi, t_lo, t_hi = ranges[k]
+            if hi <= lo:
+                continue
+            ts_d, span = times_d[lo:hi], t_hi - t_lo
         else:
-            good = (times_d >= s) & (times_d <= s + segment_size)
-        ts_d = times_d[good]
-        n_good = ts_d.numel()
-        if n_good < 1:
-            continue
-        span = float(ts_d[-1] - ts_d[0])
+            if UPSTREAM_SEMANTICS["drop_last_event"]:
+                good = (times_d >= s) & (times_d < s + segment_size)  # A2: half-open
+            else:
+                good = (times_d >= s) & (times_d <= s + segment_size)
+            ts_d = times_d[good]
+            if ts_d.numel() < 1:
+                continue
+            span = float(ts_d[-1] - ts_d[0])
         if span < 0.2 * segment_size:
             continue
         res = fold_stats_device(ts_d, freqs_d, fdots_d, nbin, nharm, flags=flags, want_profiles=return_profiles)
