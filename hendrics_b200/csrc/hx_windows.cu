@@ -183,6 +183,7 @@ extern "C" int hx_fold_windows_dev(const double *d_times, int64_t n_ev, const do
 
     // warps per CTA: as many 32-trial blocks as fit next to the tables, at most 4, no more than the trials need
     int W = (int)std::min<long long>(WIN_MAX_WARPS, (n_trials + 31) / 32);
+    if (W == 3) W = 4;  // 1, 2 or 4 warps: 3-warp CTAs load the SM's four schedulers unevenly (the 4th warp's lanes are masked)
     while (W > 1 && (size_t)nbin * 16 + (size_t)W * nbin * 128 > (size_t)di.smem_optin) W--;
     const size_t smem = (size_t)nbin * 16 + (size_t)W * nbin * 128;
     if (smem > (size_t)di.smem_optin) {
