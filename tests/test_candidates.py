@@ -274,3 +274,53 @@ def test_binary_parameter_table_golden_from_the_real_reference(tmp_path):
     assert list(df.columns) == PARAMETER_COLUMNS and not df["done"].any()
     ref = np.load(os.path.join(GOLD, "binary_parameters.npz"))["table"]
     assert np.array_equal(df[["freq", "fdot", "X", "Porb"]].to_numpy(dtype=np.float64), ref)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/hendrics"), reason="the reference tree is only in the build container")
+def test_the_reference_s_own_folding_search_runs_on_the_rebound_functions(monkeypatch):
+    """INTEGRATION.md section 3, end to end on the host side: the REAL hendrics.efsearch (imported from /root/reference with
+    its uninstallable third-party imports stubbed, as tests/golden/make_golden.py does), patched by rebind.install(),
+    calls this package's z_n_search / epoch_folding_search with its own keywords and unpacks their return tuples.  There
+    is no GPU here, so the one kernel-calling function is replaced by the oracle for the duration of the test: what is
+    checked is the glue -- signatures, keyword names, tuple shapes -- not the kernels."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+
+    finder = make_golden.StubFinder()
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, "/root/reference")
+    try:
+        hef = importlib.import_module("hendrics.efsearch")
+    finally:
+        sys.meta_path.remove(finder)
+        sys.path.remove("/root/reference")
+    import hendrics_b200.rebind as rb
+    import hendrics_b200.search as S
+    from hendrics_b200.io import EventList
+    from oracle import hx_oracle as O
+
+    def oracle_core(nharm, times, frequencies, nbin=128, segment_size=np.inf, fdots=0, **_ignored):
+        return O.folding_search_core(times, frequencies, fdots=fdots, nbin=nbin, nharm=nharm, segment_size=segment_size)
+
+    monkeypatch.setattr(S, "_folding_search", oracle_core)
+    rb.install(hef)
+    try:
+        ts = O.simulate_events(3000, 100.0, seed=4) + 8e7
+        ev = EventList(time=ts, gti=np.array([[8e7, 8e7 + 100.0]]))
+        got = hef.folding_search(ev, 9.85, 9.95, func=hef.z_n_search, oversample=2, nbin=32, nharm=2)
+        ref = O.folding_search(ts, 8e7, 9.85, 9.95, func=O.z_n_search, oversample=2, nbin=32, nharm=2)
+        assert len(got) == 4 and np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        assert got[2] == ref[2] and got[3] == ref[3]
+        got2 = hef.folding_search(ev, 9.85, 9.95, func=hef.epoch_folding_search, oversample=2, nbin=16, fdotmin=-1e-3,
+                                  fdotmax=1e-3)
+        ref2 = O.folding_search(ts, 8e7, 9.85, 9.95, func=O.epoch_folding_search, oversample=2, nbin=16, fdotmin=-1e-3,
+                                fdotmax=1e-3)
+        assert len(got2) == 6 and np.array_equal(got2[2], ref2[2]) and np.array_equal(got2[1], ref2[1])
+    finally:
+        rb.uninstall(hef)
+        stubbed = ("hendrics",) + make_golden.StubFinder.PREFIXES  # leave no stub behind for later importorskip()s
+        for name in [m for m in sys.modules if m.split(".")[0] in stubbed]:
+            del sys.modules[name]
