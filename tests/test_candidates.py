@@ -321,6 +321,9 @@ def test_the_reference_s_own_folding_search_runs_on_the_rebound_functions(monkey
         assert len(got2) == 6 and np.array_equal(got2[2], ref2[2]) and np.array_equal(got2[1], ref2[1])
     finally:
         rb.uninstall(hef)
-        stubbed = ("hendrics",) + make_golden.StubFinder.PREFIXES  # leave no stub behind for later importorskip()s
-        for name in [m for m in sys.modules if m.split(".")[0] in stubbed]:
+        from unittest.mock import MagicMock
+
+        # leave no stub (nor the stub-built hendrics) behind for later importorskip()s
+        for name in [m for m, mod in list(sys.modules.items())
+                     if m.split(".")[0] == "hendrics" or isinstance(mod, MagicMock)]:
             del sys.modules[name]
