@@ -1107,6 +1107,9 @@ def run_fold(args, wl):
             "bound": "fp64_pipe", "achieved": exec_rate * 1e-12, "peak": peak_ops * 1e-12, "unit": "TFLOP/s",
             "frac": exec_rate / peak_ops,
             "executed_fp64_ops_per_event_trial": shape["fp64_per_unit"],
+            "binding_resource": "shared-memory data pipe: one ATOMS per event*trial (26 of 32 lanes/clk/SM sustained) plus the "
+                                "broadcast event loads; see smem_pipe_frac_model and ncu.smem_pipe_pct -- the FP64 pipe is "
+                                "NOT the limiter of this kernel, frac says how busy it is",
             "smem_pipe_frac_model": smem_wf / smem_peak_wf,
             "smem_wavefronts_per_event_trial_model": shape["smem_wavefronts_per_unit"],
             "ncu": ncu, "traffic": (ncu or {}).get("dram_bytes_per_launch"),
