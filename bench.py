@@ -942,6 +942,160 @@ def run_zn(args, wl):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# orbital-demodulation fold (folding_orbital_search's T0 loop, one parameter row per launch)
+# ---------------------------------------------------------------------------------------------
+ORB = ("ORB: folding_orbital_search, one (freq, fdot, X, Porb) row: 1e6 events x 4736 trial epochs T0 per GPU, Z^2_2 nbin=64",
+       1_000_000, 1e5, 4736, 9.9, 1e-10, 3.0, 86400.0, 64, 2)
+ORB_UNIT = "event*trials/s"
+
+
+def orb_inputs(rank):
+    from hendrics_b200.fake import simulate_events
+
+    desc, n_ev, T, n_t0, freq, fdot, X, Porb, nbin, nharm = ORB
+    times = simulate_events(n_ev, T, seed=6)
+    T0s = np.random.default_rng(100 + rank).uniform(0, Porb, n_t0)  # every rank scans its own epochs (weak scaling)
+    return desc, times, T0s, freq, fdot, X, Porb, nbin, nharm
+
+
+def orb_config(desc, n_events, n_t0, nbin, nharm, n_gpus):
+    return {"workload": desc, "nbin": int(nbin), "nharm": int(nharm), "n_events": int(n_events), "n_t0_per_gpu": int(n_t0),
+            "scaling": "weak", "parallelism": f"trial epochs sharded x{n_gpus}, events replicated, no collective",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def run_orb_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import hx_oracle as O
+
+    desc, times, T0s, freq, fdot, X, Porb, nbin, nharm = orb_inputs(0)
+    n = max(2, min(T0s.size, 8 * max(args.steps, 1)))
+    t0 = time.perf_counter()
+    O.orbital_stats(times, freq, fdot, X, Porb, T0s[:n], fun=O.z_n_search, nbin=nbin, nharm=nharm)
+    dt = time.perf_counter() - t0
+    rate = times.size * n / dt
+    sample = f"oracle orbital_stats (numpy, 1 thread: the reference loops over T0 in Python), {times.size} events x {n} T0, {dt:.1f} s"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": ORB_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": orb_config(desc, times.size, T0s.size, nbin, nharm, max(args.gpus, 1)),
+            "cpu_baseline": {"value": rate, "unit": ORB_UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": ORB_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_orb(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hendrics_b200 import _cabi
+    from hendrics_b200.search import orbital_fold_stats
+
+    desc, times, T0s, freq, fdot, X, Porb, nbin, nharm = orb_inputs(rank)
+    dev = torch.device("cuda", local_rank)
+    td = torch.from_numpy(times).to(dev)
+    t0d = torch.from_numpy(T0s).to(dev)
+    stats = torch.empty(T0s.size, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    lib = _cabi.lib()
+    units_local = float(times.size) * T0s.size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        _cabi.check(lib.hx_orbital_search_dev(td.data_ptr(), td.numel(), freq, fdot, X, Porb, t0d.data_ptr(), T0s.size, nbin,
+                                              nharm, stats.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = units_local * world * args.steps / total_s
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    pin = torch.from_numpy(times).pin_memory().numpy()
+    for _ in range(2):
+        orbital_fold_stats(pin, freq, fdot, X, Porb, T0s, nbin=nbin, nharm=nharm)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = orbital_fold_stats(pin, freq, fdot, X, Porb, T0s, nbin=nbin, nharm=nharm)
+    barrier()
+    assert out.size == T0s.size
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = units_local * world * args.steps / float(e2e_s.item())
+    if rank == 0:
+        # the kernel is a long chain of dependent instructions per unit (two sin(), two IEEE divisions, the fold): its
+        # ceiling is the issue rate.  Instructions per unit come from the committed ncu capture (smsp__inst_executed.sum
+        # over the units of that launch), labelled with its file; the issue rate is 4 warp instructions per clk and SM.
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        inst_per_unit, src = None, None
+        f = os.path.join(ROOT, "profiles", "r02_ncu_orbital_top.json")
+        if os.path.exists(f):
+            try:
+                d = json.load(open(f))
+                inst_per_unit = float(str(d["smsp__inst_executed.sum"]).split()[0]) * 32.0 / (1_000_000 * 4736)
+                src = "profiles/r02_ncu_orbital_top.json (ncu --set full on tools/quick_orbital.py, same shape)"
+            except Exception:
+                inst_per_unit = None
+        clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        peak_inst = n_sm * 4 * 32 * clk  # thread-instructions per second
+        achieved = (value / world) * inst_per_unit if inst_per_unit else None
+        roofline = {"bound": "issue_slots", "achieved": achieved and achieved * 1e-12, "peak": peak_inst * 1e-12,
+                    "unit": "T thread-instructions/s", "frac": achieved and achieved / peak_inst,
+                    "instructions_per_event_trial": inst_per_unit, "instructions_source": src, "traffic": None,
+                    "kernel": "hx::orbital_fold_kernel", "kernel_ms": total_s / args.steps * 1e3}
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import hx_oracle as O
+
+            t1 = time.perf_counter()
+            O.orbital_stats(times, freq, fdot, X, Porb, T0s[:16], fun=O.z_n_search, nbin=nbin, nharm=nharm)
+            dtc = time.perf_counter() - t1
+            cpu = {"value": times.size * 16 / dtc, "unit": ORB_UNIT, "cores": 1, "kind": "port",
+                   "sample": f"oracle orbital_stats (numpy, 1 thread), {times.size} events x 16 T0, {dtc:.1f} s"}
+        line = {"metric": METRIC, "value": value, "unit": ORB_UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": orb_config(desc, times.size, T0s.size, nbin, nharm, world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": ORB_UNIT, "h2d_bytes_per_step": int(times.nbytes + T0s.nbytes),
+                        "d2h_bytes_per_step": int(T0s.size * 8), "api": "hendrics_b200.search.orbital_fold_stats per rank"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def ncu_record(wl):
     """Counters of the committed `ncu --set full` capture of this workload's bench command (profiles/), labelled with
     their source file: DRAM bytes per launch (roofline.traffic) and the pipe utilisations.  They are NOT measured
@@ -1156,7 +1310,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "ffa"] + sorted(WEIGHTED) + sorted(ZN))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "ffa", "orb"] + sorted(WEIGHTED) + sorted(ZN))
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
                     help="exact-fold workloads: strong = fixed trial grid split over the ranks (default for c3), "
                          "weak = fixed grid per GPU (default otherwise)")
@@ -1170,6 +1324,8 @@ def main():
         return run_weighted_reference(args) if args.impl == "reference" else run_weighted(args)
     if wl in ZN:
         return run_zn_reference(args, wl) if args.impl == "reference" else run_zn(args, wl)
+    if wl == "orb":
+        return run_orb_reference(args) if args.impl == "reference" else run_orb(args)
     if args.impl == "reference":
         return run_reference(args, wl)
     if wl == "c4":

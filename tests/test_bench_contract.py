@@ -12,7 +12,7 @@ KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_
         "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
 
 
-@pytest.mark.parametrize("workload", [None, "c2", "ffa", "zn1"])
+@pytest.mark.parametrize("workload", [None, "c2", "ffa", "zn1", "orb"])
 def test_reference_arm_json_line(workload):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
     if workload:
